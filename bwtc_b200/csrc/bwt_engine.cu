@@ -1,0 +1,776 @@
+// bwtc_b200/csrc/bwt_engine.cu — host orchestration + extern "C" layer (include/bwtc_cuda.h) of the
+// B200-native forward-BWT engine.  Host code is C++; all compute is in bwt_kernels.cuh.
+// No CPU fallback anywhere: if the device, an allocation or a kernel fails the call returns a negative
+// code and bwtc_cuda_last_error() says why.
+#include "../../include/bwtc_cuda.h"
+#include "bwt_kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+using namespace bwtc_b200;
+
+namespace {
+
+constexpr int RS_BLOCK = BWTC_RS_BLOCK;
+constexpr int RS_IPT64 = BWTC_RS_IPT64;
+constexpr int RS_IPT32 = BWTC_RS_IPT32;
+constexpr uint32_t RS_TILE64 = RS_BLOCK * RS_IPT64;
+constexpr uint32_t RS_TILE32 = RS_BLOCK * RS_IPT32;
+constexpr uint32_t AUX_TILE = 2048;  // k_pack_round0 / k_build_keys / k_rerank tile
+constexpr int MAX_PASSES = 8;
+constexpr uint32_t HIST_WORDS = MAX_PASSES * 256;
+constexpr uint32_t TEXT_PAD = 64;
+
+thread_local char g_err[512] = "";
+
+void set_err(char* dst, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+}
+
+inline uint32_t ceil_log2_u64(uint64_t v) {  // smallest b with 2^b >= v  (v >= 1)
+  uint32_t b = 0;
+  while ((1ull << b) < v) ++b;
+  return b;
+}
+inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+}  // namespace
+
+struct bwtc_cuda_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  uint32_t cap = 0;  // max block bytes
+  // device memory
+  uint8_t* d_in = nullptr;
+  uint8_t* d_text = nullptr;
+  uint8_t* d_out = nullptr;
+  uint32_t* d_rank = nullptr;
+  void* d_keys[2] = {nullptr, nullptr};
+  uint32_t* d_idx[2] = {nullptr, nullptr};
+  uint32_t* d_zero = nullptr;  // [ctrl CTR_WORDS][hist HIST_WORDS][tstate 2*max_aux_tiles] zeroed per round
+  uint32_t* d_status = nullptr;  // [MAX_PASSES][max_rs_tiles][256]
+  uint32_t* d_LF = nullptr;
+  size_t max_rs_tiles = 0, max_aux_tiles = 0;
+  // pinned host
+  uint32_t* h_small = nullptr;  // [ctrl CTR_WORDS][hist HIST_WORDS][LF 256]
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  int timing_detail = 0;
+  uint32_t force_chars = 0, force_keybytes = 0;
+  uint32_t debug_max_rounds = 0;  // != 0: stop refining after this many rounds (results are then wrong on purpose)
+  int last_cur = 0;               // sort buffer holding the last round's sorted records
+  bwtc_cuda_stats stats;
+  char err[512];
+  uint32_t* d_ctrl() const { return d_zero; }
+  uint32_t* d_hist() const { return d_zero + CTR_WORDS; }
+  unsigned long long* d_tstate() const { return reinterpret_cast<unsigned long long*>(d_zero + CTR_WORDS + HIST_WORDS); }
+  uint32_t* h_ctrl() const { return h_small; }
+  uint32_t* h_hist() const { return h_small + CTR_WORDS; }
+  uint32_t* h_LF() const { return h_small + CTR_WORDS + HIST_WORDS; }
+};
+
+#define CK(ctx, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      set_err((ctx)->err, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__,  \
+              cudaGetErrorString(e_));                                                             \
+      return BWTC_CUDA_ECUDA;                                                                      \
+    }                                                                                              \
+  } while (0)
+
+namespace {
+
+template <typename KeyT, int IPT, bool IOTA>
+int set_pass_attr(bwtc_cuda_ctx* ctx) {
+  CK(ctx, cudaFuncSetAttribute(k_radix_pass<KeyT, RS_BLOCK, IPT, IOTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)RadixPassSmem<KeyT, RS_BLOCK, IPT>::bytes));
+  return 0;
+}
+
+void ctx_free(bwtc_cuda_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_in); cudaFree(c->d_text); cudaFree(c->d_out); cudaFree(c->d_rank);
+  cudaFree(c->d_keys[0]); cudaFree(c->d_keys[1]); cudaFree(c->d_idx[0]); cudaFree(c->d_idx[1]);
+  cudaFree(c->d_zero); cudaFree(c->d_status); cudaFree(c->d_LF);
+  if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+  if (c->ev_end) cudaEventDestroy(c->ev_end);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+struct Round0Plan {
+  uint32_t sigma, bits, chars, keybytes, npass;
+  PackParams pp;
+};
+
+// Dense alphabet + round-0 key shape.  present[c] != 0 for every byte of the text.
+void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* present, uint32_t N, Round0Plan* pl) {
+  uint32_t sigma = 0;
+  double total = 0, H0 = 0;
+  for (int c = 0; c < 256; ++c) {
+    pl->pp.lut[c] = 0;
+    if (present[c]) { pl->pp.lut[c] = (uint8_t)sigma; ++sigma; total += (double)count[c]; }
+  }
+  for (int c = 0; c < 256; ++c)
+    if (present[c] && count[c]) { double p = (double)count[c] / total; H0 -= p * std::log2(p); }
+  const uint32_t b = sigma <= 2 ? 1 : ceil_log2_u64(sigma);
+  const uint32_t cmax64 = 64 / b, cmax32 = 32 / b;
+  uint32_t chars, keybytes;
+  if (ctx->force_chars || ctx->force_keybytes) {
+    keybytes = ctx->force_keybytes == 4 ? 4 : 8;
+    const uint32_t cmax = keybytes == 4 ? cmax32 : cmax64;
+    chars = ctx->force_chars ? ctx->force_chars : cmax;
+    if (chars > cmax) chars = cmax;
+    if (chars < 1) chars = 1;
+  } else {
+    // an i.i.d. source of entropy H0 separates all but ~2^-6 of N suffixes after need/H0 characters;
+    // sources with memory (H_rate < H0) simply leave more suffixes live for the doubling rounds.
+    const double need = std::log2((double)N + 1.0) + 6.0;
+    double cn = std::ceil(need / (H0 > 1e-3 ? H0 : 1e-3));
+    if (cn > 64) cn = 64;
+    const uint32_t c_need = (uint32_t)cn < 1 ? 1 : (uint32_t)cn;
+    if (c_need <= cmax32) {
+      keybytes = 4;
+      const uint32_t np = div_up((uint64_t)c_need * b, 8);
+      chars = (8 * np) / b;
+      if (chars > cmax32) chars = cmax32;
+    } else {
+      keybytes = 8;
+      const uint32_t np = div_up((uint64_t)(c_need < cmax64 ? c_need : cmax64) * b, 8);
+      chars = (8 * np) / b;
+      if (chars > cmax64) chars = cmax64;
+    }
+  }
+  pl->sigma = sigma;
+  pl->bits = b;
+  pl->chars = chars;
+  pl->keybytes = keybytes;
+  pl->npass = div_up((uint64_t)chars * b, 8);
+  pl->pp.bits = b;
+  pl->pp.chars = chars;
+}
+
+struct PassTimer {
+  bwtc_cuda_ctx* ctx;
+  size_t used = 0;
+  int begin() {
+    if (!ctx->timing_detail) return 0;
+    if (used + 2 > ctx->ev_pool.size()) return 0;
+    CK(ctx, cudaEventRecord(ctx->ev_pool[used], ctx->stream));
+    return 0;
+  }
+  int end() {
+    if (!ctx->timing_detail) return 0;
+    if (used + 2 > ctx->ev_pool.size()) return 0;
+    CK(ctx, cudaEventRecord(ctx->ev_pool[used + 1], ctx->stream));
+    used += 2;
+    return 0;
+  }
+};
+
+// One LSD radix sort of m records: executes the digit passes whose bit is set in pass_mask, ping-ponging
+// between buffer 0 and 1.  Records start in buffer `cur` (0); returns the buffer holding the result.
+template <typename KeyT, int IPT>
+int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota, uint32_t iota_top, int* cur_io,
+             PassTimer* pt, uint32_t* passes_done) {
+  constexpr uint32_t TILE = RS_BLOCK * IPT;
+  const uint32_t tiles = div_up(m, TILE);
+  const size_t smem = RadixPassSmem<KeyT, RS_BLOCK, IPT>::bytes;
+  int cur = *cur_io;
+  bool iota = first_iota;
+  uint32_t done = 0;
+  for (int p = 0; p < MAX_PASSES; ++p) {
+    if (!((pass_mask >> p) & 1u)) continue;
+    const KeyT* kin = static_cast<const KeyT*>(ctx->d_keys[cur]);
+    KeyT* kout = static_cast<KeyT*>(ctx->d_keys[cur ^ 1]);
+    uint32_t* status = ctx->d_status + (size_t)p * ctx->max_rs_tiles * 256u;
+    if (pt->begin()) return BWTC_CUDA_ECUDA;
+    if (iota)
+      k_radix_pass<KeyT, RS_BLOCK, IPT, true><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
+          kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
+          CTR_PASS0 + p, iota_top);
+    else
+      k_radix_pass<KeyT, RS_BLOCK, IPT, false><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
+          kin, ctx->d_idx[cur], kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
+          CTR_PASS0 + p, iota_top);
+    CK(ctx, cudaGetLastError());
+    if (pt->end()) return BWTC_CUDA_ECUDA;
+    ctx->stats.kernel_launches++;
+    const uint64_t rec = sizeof(KeyT) + 4;
+    ctx->stats.algorithmic_bytes += (uint64_t)m * (2 * rec - (iota ? 4 : 0));
+    ctx->stats.sort_bytes += (uint64_t)m * (2 * rec - (iota ? 4 : 0));
+    ctx->stats.sort_launches++;
+    iota = false;
+    cur ^= 1;
+    ++done;
+  }
+  *cur_io = cur;
+  *passes_done = done;
+  return 0;
+}
+
+int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t rs_tile, uint32_t pass_mask) {
+  const uint32_t aux_tiles = div_up(m, AUX_TILE);
+  CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)aux_tiles * 8, ctx->stream));
+  const uint32_t tiles = div_up(m, rs_tile);
+  for (int p = 0; p < MAX_PASSES; ++p)
+    if ((pass_mask >> p) & 1u)
+      CK(ctx, cudaMemsetAsync(ctx->d_status + (size_t)p * ctx->max_rs_tiles * 256u, 0, (size_t)tiles * 1024u, ctx->stream));
+  return 0;
+}
+
+// The engine proper.  block_mode: in = X (n block bytes), result n bytes.  raw: in = T (n bytes), result n bytes.
+// in_dev / out_dev: device pointers supplied by the caller (or nullptr -> staged through the context).
+int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, uint8_t* h_out, const uint8_t* in_dev,
+                      uint8_t* out_dev, uint32_t n, uint32_t* LF, uint32_t nLF, uint32_t* freqs) {
+  ctx->err[0] = 0;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) {
+    set_err(ctx->err, "cudaSetDevice(%d) failed", ctx->device);
+    return BWTC_CUDA_ECUDA;
+  }
+  const uint32_t N = block_mode ? n + 1 : n;
+  if (n > ctx->cap) {
+    set_err(ctx->err, "block of %u bytes exceeds context capacity %u", n, ctx->cap);
+    return BWTC_CUDA_ETOOBIG;
+  }
+  if (nLF < 1 || nLF > 256 || nLF > N || !LF) {
+    set_err(ctx->err, "bad nLFpowers %u for %u suffixes", nLF, N);
+    return BWTC_CUDA_EARG;
+  }
+  cudaStream_t st = ctx->stream;
+  bwtc_cuda_stats& S = ctx->stats;
+  memset(&S, 0, sizeof(S));
+  S.n_suffixes = N;
+  PassTimer pt{ctx};
+
+  // ---- input
+  const uint8_t* d_src = in_dev;
+  if (!in_dev) {
+    CK(ctx, cudaMemcpyAsync(ctx->d_in, h_in, n, cudaMemcpyHostToDevice, st));
+    d_src = ctx->d_in;
+  }
+  uint8_t* d_dst = out_dev ? out_dev : ctx->d_out;
+  CK(ctx, cudaEventRecord(ctx->ev_begin, st));
+
+  // ---- byte histogram (+ reversed, sentinel-terminated text in block mode)
+  CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)(CTR_WORDS + HIST_WORDS) * 4, st));
+  const uint8_t* d_text;
+  const int pgrid = ctx->sm_count * 8;
+  if (block_mode) {
+    const uint32_t padded_words = div_up((uint64_t)N + TEXT_PAD, 4);
+    k_prep_block<<<pgrid, 256, 0, st>>>(d_src, n, ctx->d_text, padded_words, ctx->d_hist());
+    d_text = ctx->d_text;
+    S.algorithmic_bytes += (uint64_t)n + N;
+  } else {
+    k_hist_bytes<<<pgrid, 256, 0, st>>>(d_src, N - 1, ctx->d_hist());
+    d_text = d_src;
+    S.algorithmic_bytes += (uint64_t)N;
+  }
+  CK(ctx, cudaGetLastError());
+  S.kernel_launches++;
+  CK(ctx, cudaMemcpyAsync(ctx->h_hist(), ctx->d_hist(), 256 * 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+
+  uint64_t count[256];
+  bool present[256];
+  for (int c = 0; c < 256; ++c) {
+    count[c] = ctx->h_hist()[c];
+    present[c] = count[c] != 0;
+    if (freqs) freqs[c] += ctx->h_hist()[c];
+  }
+  const uint8_t last = block_mode ? (uint8_t)0 : h_in[N - 1];
+  present[last] = true;
+  count[last] += 1;
+
+  Round0Plan pl;
+  plan_round0(ctx, count, present, N, &pl);
+  S.sigma = pl.sigma;
+  S.bits_per_char = pl.bits;
+  S.chars_round0 = pl.chars;
+  S.key_bytes_round0 = pl.keybytes;
+
+  // ---- round 0: pack keys (+ all digit histograms), sort, re-rank
+  const uint32_t rs_tile0 = pl.keybytes == 4 ? RS_TILE32 : RS_TILE64;
+  const uint32_t all0 = (1u << pl.npass) - 1u;
+  if (zero_round_state(ctx, N, rs_tile0, all0)) return BWTC_CUDA_ECUDA;
+  {
+    const uint32_t ptiles = div_up(N, AUX_TILE);
+    const int grid = (int)(ptiles < (uint32_t)(ctx->sm_count * 4) ? ptiles : (uint32_t)(ctx->sm_count * 4));
+    if (pl.keybytes == 4)
+      k_pack_round0<uint32_t><<<grid, 256, 0, st>>>(d_text, N, static_cast<uint32_t*>(ctx->d_keys[0]), pl.pp,
+                                                     ctx->d_hist(), (int)pl.npass, ptiles);
+    else
+      k_pack_round0<unsigned long long><<<grid, 256, 0, st>>>(d_text, N, static_cast<unsigned long long*>(ctx->d_keys[0]),
+                                                               pl.pp, ctx->d_hist(), (int)pl.npass, ptiles);
+    CK(ctx, cudaGetLastError());
+    S.kernel_launches++;
+    S.algorithmic_bytes += (uint64_t)N + (uint64_t)N * pl.keybytes;
+  }
+  CK(ctx, cudaMemcpyAsync(ctx->h_hist(), ctx->d_hist(), pl.npass * 256 * 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  uint32_t mask0 = 0;
+  for (uint32_t p = 0; p < pl.npass; ++p) {
+    bool constant = false;
+    for (int d = 0; d < 256; ++d)
+      if (ctx->h_hist()[p * 256 + d] == N) { constant = true; break; }
+    if (!constant) mask0 |= 1u << p;
+  }
+  if (!mask0) mask0 = 1u;  // the sort must run at least once: it is what materialises the suffix ids
+  int cur = 0;
+  uint32_t pdone = 0;
+  int rc;
+  if (pl.keybytes == 4) rc = run_sort<uint32_t, RS_IPT32>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone);
+  else rc = run_sort<unsigned long long, RS_IPT64>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone);
+  if (rc) return rc;
+  S.live[0] = N;
+  S.passes[0] = pdone;
+  S.prefix_len[0] = 0;
+  S.rounds = 1;
+  {
+    RerankParams rp;
+    rp.m = N;
+    rp.short_thresh = pl.chars > N ? 0u : N - pl.chars + 1u;
+    rp.lo_bits = 0;
+    const uint32_t tiles = div_up(N, AUX_TILE);
+    if (pl.keybytes == 4)
+      k_rerank<uint32_t, true><<<tiles, 256, 0, st>>>(static_cast<const uint32_t*>(ctx->d_keys[cur]), ctx->d_idx[cur],
+                                                      ctx->d_rank, rp, ctx->d_tstate(), ctx->d_ctrl());
+    else
+      k_rerank<unsigned long long, true><<<tiles, 256, 0, st>>>(static_cast<const unsigned long long*>(ctx->d_keys[cur]),
+                                                                ctx->d_idx[cur], ctx->d_rank, rp, ctx->d_tstate(),
+                                                                ctx->d_ctrl());
+    CK(ctx, cudaGetLastError());
+    S.kernel_launches++;
+    S.algorithmic_bytes += (uint64_t)N * (pl.keybytes + 4) + (uint64_t)N * 4;
+  }
+  CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_WORDS * 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  if (ctx->h_ctrl()[CTR_ERR]) {
+    set_err(ctx->err, "look-back watchdog fired in round 0 (code %u)", ctx->h_ctrl()[CTR_ERR]);
+    return BWTC_CUDA_EINTERNAL;
+  }
+  uint32_t live = ctx->h_ctrl()[CTR_LIVE];
+  ctx->last_cur = cur;
+
+  // ---- doubling rounds
+  const int lo_bits = (int)ceil_log2_u64((uint64_t)N + 1);
+  const int hi_bits = (int)ceil_log2_u64((uint64_t)N);
+  const uint32_t npassd = div_up((uint64_t)(lo_bits + hi_bits), 8);
+  const uint32_t maskd = (1u << npassd) - 1u;
+  uint64_t h = pl.chars;
+  while (live > 0) {
+    if (ctx->debug_max_rounds && S.rounds >= ctx->debug_max_rounds) break;
+    if (S.rounds >= BWTC_CUDA_MAX_ROUNDS || h >= 2ull * N + 2) {
+      set_err(ctx->err, "prefix doubling did not converge (round %u, h %llu, live %u)", S.rounds, (unsigned long long)h, live);
+      return BWTC_CUDA_EINTERNAL;
+    }
+    const uint32_t r = S.rounds;
+    const uint32_t m = live;
+    if (zero_round_state(ctx, m, RS_TILE64, maskd)) return BWTC_CUDA_ECUDA;
+    {
+      const uint32_t btiles = div_up(N, AUX_TILE);
+      const int grid = (int)(btiles < (uint32_t)(ctx->sm_count * 4) ? btiles : (uint32_t)(ctx->sm_count * 4));
+      k_build_keys<<<grid, 256, 0, st>>>(ctx->d_rank, N, (uint32_t)(h > 0xFFFFFFFFull ? 0xFFFFFFFFull : h), lo_bits,
+                                         static_cast<unsigned long long*>(ctx->d_keys[0]), ctx->d_idx[0], ctx->d_ctrl(),
+                                         ctx->d_hist(), (int)npassd, btiles);
+      CK(ctx, cudaGetLastError());
+      S.kernel_launches++;
+      S.algorithmic_bytes += (uint64_t)N * 4 + (uint64_t)m * 12;
+    }
+    cur = 0;
+    rc = run_sort<unsigned long long, RS_IPT64>(ctx, m, maskd, false, 0, &cur, &pt, &pdone);
+    if (rc) return rc;
+    {
+      RerankParams rp;
+      rp.m = m;
+      rp.short_thresh = 0;
+      rp.lo_bits = lo_bits;
+      k_rerank<unsigned long long, false><<<div_up(m, AUX_TILE), 256, 0, st>>>(
+          static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp, ctx->d_tstate(),
+          ctx->d_ctrl());
+      CK(ctx, cudaGetLastError());
+      S.kernel_launches++;
+      S.algorithmic_bytes += (uint64_t)m * 12 + (uint64_t)m * 4;
+    }
+    CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_WORDS * 4, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    if (ctx->h_ctrl()[CTR_ERR]) {
+      set_err(ctx->err, "look-back watchdog fired in round %u (code %u)", r, ctx->h_ctrl()[CTR_ERR]);
+      return BWTC_CUDA_EINTERNAL;
+    }
+    if (ctx->h_ctrl()[CTR_CURSOR] != m) {
+      set_err(ctx->err, "round %u: k_build_keys emitted %u records, expected %u", r, ctx->h_ctrl()[CTR_CURSOR], m);
+      return BWTC_CUDA_EINTERNAL;
+    }
+    S.live[r] = m;
+    S.passes[r] = pdone;
+    S.prefix_len[r] = (uint32_t)(h > 0xFFFFFFFFull ? 0xFFFFFFFFull : h);
+    S.rounds = r + 1;
+    live = ctx->h_ctrl()[CTR_LIVE];
+    ctx->last_cur = cur;
+    h *= 2;
+  }
+
+  // ---- final: fused BWT emission + pidx + LFpowers (+ hole fill)
+  {
+    const uint32_t tiles = div_up(N, 256 * 8);
+    const int grid = (int)(tiles < (uint32_t)(ctx->sm_count * 8) ? tiles : (uint32_t)(ctx->sm_count * 8));
+    k_final<<<grid > 0 ? grid : 1, 256, 0, st>>>(ctx->d_rank, d_text, N, d_dst, block_mode ? 1 : 0, ctx->d_LF, nLF);
+    CK(ctx, cudaGetLastError());
+    S.kernel_launches++;
+    S.algorithmic_bytes += (uint64_t)N * 6;
+  }
+  CK(ctx, cudaEventRecord(ctx->ev_end, st));
+  CK(ctx, cudaMemcpyAsync(ctx->h_LF(), ctx->d_LF, nLF * 4, cudaMemcpyDeviceToHost, st));
+  if (!out_dev) CK(ctx, cudaMemcpyAsync(h_out, ctx->d_out, n, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  for (uint32_t j = 0; j < nLF; ++j) LF[j] = ctx->h_LF()[j];
+  float ms = 0;
+  CK(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+  S.gpu_ms = ms;
+  if (ctx->timing_detail) {
+    float tot = 0;
+    for (size_t i = 0; i + 1 < pt.used; i += 2) {
+      float t = 0;
+      CK(ctx, cudaEventElapsedTime(&t, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+      tot += t;
+    }
+    S.sort_ms = tot;
+  }
+  return (int64_t)LF[0];
+}
+
+}  // namespace
+
+// =====================================================================================================
+// extern "C"
+// =====================================================================================================
+extern "C" {
+
+int bwtc_cuda_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_err(g_err, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return BWTC_CUDA_ECUDA;
+  }
+  return n;
+}
+
+#define BWTC_STR2(x) #x
+#define BWTC_STR(x) BWTC_STR2(x)
+const char* bwtc_cuda_version(void) {
+  return "bwtc_b200 0.1 sm_100a radix-pass BLOCK=" BWTC_STR(BWTC_RS_BLOCK) " IPT64=" BWTC_STR(BWTC_RS_IPT64)
+         " IPT32=" BWTC_STR(BWTC_RS_IPT32);
+}
+
+const char* bwtc_cuda_global_error(void) { return g_err; }
+
+int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_bytes) {
+  if (!out || max_block_bytes == 0) { set_err(g_err, "bad arguments"); return BWTC_CUDA_EARG; }
+  if (max_block_bytes > BWTC_CUDA_MAX_BLOCK) { set_err(g_err, "max_block_bytes above engine limit"); return BWTC_CUDA_ETOOBIG; }
+  *out = nullptr;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { set_err(g_err, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); return BWTC_CUDA_ECUDA; }
+  bwtc_cuda_ctx* c = new (std::nothrow) bwtc_cuda_ctx();
+  if (!c) { set_err(g_err, "out of host memory"); return BWTC_CUDA_EALLOC; }
+  c->device = device;
+  c->cap = max_block_bytes;
+  c->err[0] = 0;
+  memset(&c->stats, 0, sizeof(c->stats));
+  const size_t N = (size_t)max_block_bytes + 1;
+  const uint32_t min_tile = RS_TILE64 < RS_TILE32 ? RS_TILE64 : RS_TILE32;
+  c->max_rs_tiles = div_up(N, min_tile);
+  c->max_aux_tiles = div_up(N, AUX_TILE);
+  int rc = 0;
+#define ALLOC(ptr, bytes)                                                                       \
+  do {                                                                                          \
+    if (!rc) {                                                                                  \
+      e = cudaMalloc((void**)&(ptr), (bytes));                                                  \
+      if (e != cudaSuccess) {                                                                   \
+        set_err(g_err, "cudaMalloc(%zu bytes) for " #ptr ": %s", (size_t)(bytes), cudaGetErrorString(e)); \
+        rc = BWTC_CUDA_EALLOC;                                                                  \
+      }                                                                                         \
+    }                                                                                           \
+  } while (0)
+  int sm = 0;
+  if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sm > 0) c->sm_count = sm;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { set_err(g_err, "cudaStreamCreate: %s", cudaGetErrorString(e)); rc = BWTC_CUDA_ECUDA; }
+  const size_t padded = ((N + TEXT_PAD + 15) / 16) * 16 + 16;
+  ALLOC(c->d_in, padded);
+  ALLOC(c->d_text, padded);
+  ALLOC(c->d_out, padded);
+  ALLOC(c->d_rank, (N + 1) * 4);
+  ALLOC(c->d_keys[0], N * 8);
+  ALLOC(c->d_keys[1], N * 8);
+  ALLOC(c->d_idx[0], N * 4);
+  ALLOC(c->d_idx[1], N * 4);
+  ALLOC(c->d_zero, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + c->max_aux_tiles * 8 + 64);
+  ALLOC(c->d_status, (size_t)MAX_PASSES * c->max_rs_tiles * 1024u);
+  ALLOC(c->d_LF, 256 * 4);
+#undef ALLOC
+  if (!rc) {
+    e = cudaMallocHost((void**)&c->h_small, (size_t)(CTR_WORDS + HIST_WORDS + 256) * 4);
+    if (e != cudaSuccess) { set_err(g_err, "cudaMallocHost: %s", cudaGetErrorString(e)); rc = BWTC_CUDA_EALLOC; }
+  }
+  if (!rc && (cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess)) {
+    set_err(g_err, "cudaEventCreate failed");
+    rc = BWTC_CUDA_ECUDA;
+  }
+  if (!rc) {
+    int r2 = 0;
+    r2 |= set_pass_attr<uint32_t, RS_IPT32, true>(c);
+    r2 |= set_pass_attr<uint32_t, RS_IPT32, false>(c);
+    r2 |= set_pass_attr<unsigned long long, RS_IPT64, true>(c);
+    r2 |= set_pass_attr<unsigned long long, RS_IPT64, false>(c);
+    if (r2) { set_err(g_err, "%s", c->err); rc = BWTC_CUDA_ECUDA; }
+  }
+  if (rc) { ctx_free(c); return rc; }
+  *out = c;
+  return 0;
+}
+
+void bwtc_cuda_ctx_destroy(bwtc_cuda_ctx* ctx) { ctx_free(ctx); }
+
+const char* bwtc_cuda_last_error(const bwtc_cuda_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+int bwtc_cuda_get_stats(const bwtc_cuda_ctx* ctx, bwtc_cuda_stats* out) {
+  if (!ctx || !out) return BWTC_CUDA_EARG;
+  *out = ctx->stats;
+  return 0;
+}
+
+int bwtc_cuda_ctx_set_round0(bwtc_cuda_ctx* ctx, uint32_t chars, uint32_t key_bytes) {
+  if (!ctx || (key_bytes != 0 && key_bytes != 4 && key_bytes != 8) || chars > 64) return BWTC_CUDA_EARG;
+  ctx->force_chars = chars;
+  ctx->force_keybytes = key_bytes;
+  return 0;
+}
+
+int bwtc_cuda_ctx_set_timing(bwtc_cuda_ctx* ctx, int detail) {
+  if (!ctx) return BWTC_CUDA_EARG;
+  if (detail && ctx->ev_pool.empty()) {
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return BWTC_CUDA_ECUDA;
+    ctx->ev_pool.resize(2 * MAX_PASSES * BWTC_CUDA_MAX_ROUNDS);
+    for (auto& ev : ctx->ev_pool)
+      if (cudaEventCreate(&ev) != cudaSuccess) { set_err(ctx->err, "cudaEventCreate failed"); return BWTC_CUDA_ECUDA; }
+  }
+  ctx->timing_detail = detail;
+  return 0;
+}
+
+/* Debug / test hooks (declared in include/bwtc_cuda.h): stop after `max_rounds` sort rounds and read
+ * back engine buffers so a harness can check every stage against a CPU restatement. */
+int bwtc_cuda_ctx_set_debug(bwtc_cuda_ctx* ctx, uint32_t max_rounds) {
+  if (!ctx) return BWTC_CUDA_EARG;
+  ctx->debug_max_rounds = max_rounds;
+  return 0;
+}
+
+int bwtc_cuda_debug_read(bwtc_cuda_ctx* ctx, int which, uint64_t offset_bytes, void* dst, uint64_t bytes) {
+  if (!ctx || !dst) return BWTC_CUDA_EARG;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return BWTC_CUDA_ECUDA;
+  const uint8_t* src = nullptr;
+  switch (which) {
+    case 0: src = ctx->d_text; break;
+    case 1: src = reinterpret_cast<const uint8_t*>(ctx->d_rank); break;
+    case 2: src = static_cast<const uint8_t*>(ctx->d_keys[ctx->last_cur]); break;
+    case 3: src = reinterpret_cast<const uint8_t*>(ctx->d_idx[ctx->last_cur]); break;
+    case 4: src = static_cast<const uint8_t*>(ctx->d_keys[ctx->last_cur ^ 1]); break;
+    case 5: src = reinterpret_cast<const uint8_t*>(ctx->d_idx[ctx->last_cur ^ 1]); break;
+    case 6: src = reinterpret_cast<const uint8_t*>(ctx->d_zero); break;
+    case 7: src = ctx->d_in; break;
+    default: return BWTC_CUDA_EARG;
+  }
+  CK(ctx, cudaMemcpy(dst, src + offset_bytes, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int64_t bwtc_cuda_divbwtf(bwtc_cuda_ctx* ctx, const uint8_t* T, uint8_t* U, uint32_t n, uint32_t* LFpowers,
+                          uint32_t nLFpowers, uint32_t* freqs) {
+  if (!ctx) { set_err(g_err, "null context"); return BWTC_CUDA_EARG; }
+  if (!T || !U) { set_err(ctx->err, "null T or U"); return BWTC_CUDA_EARG; }  // divsufsort.c:488
+  if (n <= 1) {  // divsufsort.c:489: trivial inputs never reach the sort; LFpowers stays untouched
+    if (n == 1) U[0] = T[0];
+    return n;
+  }
+  return run_transform(ctx, false, T, U, nullptr, nullptr, n, LFpowers, nLFpowers, freqs);
+}
+
+int64_t bwtc_cuda_divbwt(bwtc_cuda_ctx* ctx, const uint8_t* T, uint8_t* U, uint32_t n, uint32_t* LFpowers,
+                         uint32_t nLFpowers) {
+  return bwtc_cuda_divbwtf(ctx, T, U, n, LFpowers, nLFpowers, nullptr);
+}
+
+int64_t bwtc_cuda_bwt_block(bwtc_cuda_ctx* ctx, uint8_t* block, uint32_t n, uint32_t* LFpowers, uint32_t nLFpowers,
+                            uint32_t* freqs) {
+  if (!ctx) { set_err(g_err, "null context"); return BWTC_CUDA_EARG; }
+  if (!block || n == 0) { set_err(ctx->err, "null or empty block"); return BWTC_CUDA_EARG; }
+  return run_transform(ctx, true, block, block, nullptr, nullptr, n, LFpowers, nLFpowers, freqs);
+}
+
+int64_t bwtc_cuda_bwt_block_device(bwtc_cuda_ctx* ctx, const void* d_in, void* d_out, uint32_t n, uint32_t* LFpowers,
+                                   uint32_t nLFpowers, uint32_t* freqs) {
+  if (!ctx) { set_err(g_err, "null context"); return BWTC_CUDA_EARG; }
+  if (!d_in || !d_out || n == 0) { set_err(ctx->err, "null or empty block"); return BWTC_CUDA_EARG; }
+  return run_transform(ctx, true, nullptr, nullptr, static_cast<const uint8_t*>(d_in), static_cast<uint8_t*>(d_out), n,
+                       LFpowers, nLFpowers, freqs);
+}
+
+uint32_t bwtc_cuda_num_starting_points(uint32_t block_bytes, uint32_t starts) {
+  if (starts < 1) starts = 1; else if (starts > 256) starts = 256;  // BWTManager.cpp:60-64
+  return block_bytes <= 256 ? 1u : starts;                         // BWTBlock.cpp:104-108
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// Batched pipeline: `depth` contexts on one GPU, one host worker per context, blocks handed out in order.
+// Replaces the synchronous per-slice loop of Compressor::compress (Compressor.cpp:100-109) for the BWT
+// stage; results are delivered by block index so a caller can entropy-code strictly in file order.
+// =====================================================================================================
+struct bwtc_cuda_pipeline {
+  int device = 0;
+  std::vector<bwtc_cuda_ctx*> ctxs;
+  cudaStream_t tstream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ev_done;
+  char err[512];
+};
+
+extern "C" {
+
+void bwtc_cuda_pipeline_destroy(bwtc_cuda_pipeline* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  for (bwtc_cuda_ctx* c : p->ctxs) ctx_free(c);
+  for (cudaEvent_t e : p->ev_done) cudaEventDestroy(e);
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
+  if (p->tstream) cudaStreamDestroy(p->tstream);
+  delete p;
+}
+
+int bwtc_cuda_pipeline_create(bwtc_cuda_pipeline** out, int device, int depth, uint32_t max_block_bytes) {
+  if (!out || depth < 1 || depth > 64) { set_err(g_err, "bad arguments"); return BWTC_CUDA_EARG; }
+  *out = nullptr;
+  bwtc_cuda_pipeline* p = new (std::nothrow) bwtc_cuda_pipeline();
+  if (!p) return BWTC_CUDA_EALLOC;
+  p->device = device;
+  p->err[0] = 0;
+  for (int i = 0; i < depth; ++i) {
+    bwtc_cuda_ctx* c = nullptr;
+    int rc = bwtc_cuda_ctx_create(&c, device, max_block_bytes);
+    if (rc) { bwtc_cuda_pipeline_destroy(p); return rc; }
+    p->ctxs.push_back(c);
+  }
+  bool ok = cudaStreamCreateWithFlags(&p->tstream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&p->ev0) == cudaSuccess && cudaEventCreate(&p->ev1) == cudaSuccess;
+  p->ev_done.resize(depth, nullptr);
+  for (int i = 0; ok && i < depth; ++i) ok = cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { set_err(g_err, "pipeline stream/event creation failed"); bwtc_cuda_pipeline_destroy(p); return BWTC_CUDA_ECUDA; }
+  *out = p;
+  return 0;
+}
+
+const char* bwtc_cuda_pipeline_error(const bwtc_cuda_pipeline* p) { return p ? p->err : g_err; }
+
+int bwtc_cuda_pipeline_set_round0(bwtc_cuda_pipeline* p, uint32_t chars, uint32_t key_bytes) {
+  if (!p) return BWTC_CUDA_EARG;
+  for (bwtc_cuda_ctx* c : p->ctxs) {
+    int rc = bwtc_cuda_ctx_set_round0(c, chars, key_bytes);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int bwtc_cuda_pipeline_set_timing(bwtc_cuda_pipeline* p, int detail) {
+  if (!p) return BWTC_CUDA_EARG;
+  for (bwtc_cuda_ctx* c : p->ctxs) {
+    int rc = bwtc_cuda_ctx_set_timing(c, detail);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int bwtc_cuda_pipeline_run(bwtc_cuda_pipeline* p, const uint8_t* const* in, uint8_t* const* out, const uint32_t* sizes,
+                           uint32_t nblocks, uint32_t starts, int on_device, uint32_t* LFpowers, uint32_t* nLF,
+                           uint32_t* freqs, bwtc_cuda_stats* stats) {
+  if (!p || !in || !out || !sizes || !LFpowers || !nLF) { if (p) set_err(p->err, "bad arguments"); return BWTC_CUDA_EARG; }
+  p->err[0] = 0;
+  std::atomic<uint32_t> next(0);
+  std::atomic<int> first_err(0);
+  std::mutex err_mu;
+  auto worker = [&](bwtc_cuda_ctx* c) {
+    for (;;) {
+      const uint32_t i = next.fetch_add(1);
+      if (i >= nblocks || first_err.load()) break;
+      const uint32_t n = sizes[i];
+      const uint32_t k = bwtc_cuda_num_starting_points(n, starts);
+      nLF[i] = k;
+      uint32_t* lf = LFpowers + (size_t)i * 256;
+      uint32_t* fr = freqs ? freqs + (size_t)i * 256 : nullptr;
+      int64_t rc;
+      if (on_device) {
+        rc = bwtc_cuda_bwt_block_device(c, in[i], out[i], n, lf, k, fr);
+      } else {
+        if (!in[i] || !out[i] || n == 0) { set_err(c->err, "null or empty block %u", i); rc = BWTC_CUDA_EARG; }
+        else rc = run_transform(c, true, in[i], out[i], nullptr, nullptr, n, lf, k, fr);
+      }
+      if (stats) stats[i] = c->stats;
+      if (rc < 0) {
+        std::lock_guard<std::mutex> g(err_mu);
+        if (!first_err.load()) { first_err.store((int)rc); set_err(p->err, "block %u: %s", i, c->err); }
+        break;
+      }
+    }
+  };
+  std::vector<std::thread> threads;
+  for (size_t t = 1; t < p->ctxs.size(); ++t) threads.emplace_back(worker, p->ctxs[t]);
+  worker(p->ctxs[0]);
+  for (std::thread& t : threads) t.join();
+  return first_err.load();
+}
+
+int bwtc_cuda_pipeline_timing_begin(bwtc_cuda_pipeline* p) {
+  if (!p) return BWTC_CUDA_EARG;
+  if (cudaSetDevice(p->device) != cudaSuccess) return BWTC_CUDA_ECUDA;
+  if (cudaEventRecord(p->ev0, p->tstream) != cudaSuccess) return BWTC_CUDA_ECUDA;
+  for (bwtc_cuda_ctx* c : p->ctxs)
+    if (cudaStreamWaitEvent(c->stream, p->ev0, 0) != cudaSuccess) return BWTC_CUDA_ECUDA;
+  return 0;
+}
+
+float bwtc_cuda_pipeline_timing_end(bwtc_cuda_pipeline* p) {
+  if (!p) return (float)BWTC_CUDA_EARG;
+  if (cudaSetDevice(p->device) != cudaSuccess) return (float)BWTC_CUDA_ECUDA;
+  for (size_t i = 0; i < p->ctxs.size(); ++i) {
+    if (cudaEventRecord(p->ev_done[i], p->ctxs[i]->stream) != cudaSuccess) return (float)BWTC_CUDA_ECUDA;
+    if (cudaStreamWaitEvent(p->tstream, p->ev_done[i], 0) != cudaSuccess) return (float)BWTC_CUDA_ECUDA;
+  }
+  if (cudaEventRecord(p->ev1, p->tstream) != cudaSuccess) return (float)BWTC_CUDA_ECUDA;
+  if (cudaEventSynchronize(p->ev1) != cudaSuccess) return (float)BWTC_CUDA_ECUDA;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) != cudaSuccess) return (float)BWTC_CUDA_ECUDA;
+  return ms;
+}
+
+}  // extern "C"

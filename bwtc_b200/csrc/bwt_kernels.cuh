@@ -1,0 +1,671 @@
+// bwtc_b200/csrc/bwt_kernels.cuh — hand-written sm_100a kernels of the forward-BWT engine.
+//
+// Algorithm: suffix array by prefix doubling, never materialised as an array —
+// the engine keeps the inverse suffix array rank[] (ISA) and refines it:
+//   round 0   : key(i) = first c characters of suffix i as dense b-bit codes (k_pack_round0),
+//               LSD radix sort of (key, suffix id) with one-sweep digit passes (k_radix_pass),
+//               segmented re-rank (k_rerank<ROUND0>): rank[i] = index of i's group head, singletons
+//               flagged RANK_DONE.
+//   round r>0 : text-order scan of rank[] emits a packed (rank[i], rank[i+h]) 64-bit key for every
+//               still-live suffix (k_build_keys, compaction fused), same radix sort, k_rerank<false>.
+//   final     : out[rank[i]] = T[i-1] fused with pidx / LFpowers extraction and the bwtc hole-fill
+//               (k_final).
+// All of this replaces sort_typeBstar + sssort + trsort + construct_BWT of the reference
+// (bwtransforms/divsufsort.c:38-192,328-404; sssort.c:746-815; trsort.c:554-586) — it is NOT a port of
+// them: no B*-suffix classification, no induced sorting, no introsort.
+//
+// Everything is integer / byte work bound by HBM bandwidth; no tensor cores are used on purpose.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bwtc_b200 {
+
+constexpr uint32_t RANK_DONE = 0x80000000u;  // bit 31 of rank[i]: suffix i is alone in its group (final)
+constexpr uint32_t RANK_MASK = 0x7FFFFFFFu;
+
+// ---- control words (one uint32 array per context, zeroed by a memset at the start of every round)
+constexpr int CTR_PASS0 = 0;       // [0..15]  dynamic tile counters of the radix passes of this round
+constexpr int CTR_RERANK = 16;     // dynamic tile counter of k_rerank
+constexpr int CTR_CURSOR = 17;     // output cursor of k_build_keys (== number of live records emitted)
+constexpr int CTR_LIVE = 18;       // records still in non-singleton groups after k_rerank
+constexpr int CTR_ERR = 19;        // != 0: a look-back watchdog fired (engine returns BWTC_CUDA_EINTERNAL)
+constexpr int CTR_WORDS = 32;
+
+// look-back status words of the radix pass: 2 flag bits + 30-bit count
+constexpr uint32_t LB_AGG = 0x40000000u, LB_PREFIX = 0x80000000u, LB_VALUE = 0x3FFFFFFFu;
+constexpr uint32_t LB_SPIN_LIMIT = 1u << 24;
+
+#ifndef BWTC_RS_BLOCK
+#define BWTC_RS_BLOCK 256
+#endif
+#ifndef BWTC_RS_IPT64
+#define BWTC_RS_IPT64 16
+#endif
+#ifndef BWTC_RS_IPT32
+#define BWTC_RS_IPT32 16
+#endif
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Lanes of the warp whose 8-bit digit equals mine (8 ballots; the multi-split primitive of the sort).
+__device__ __forceinline__ uint32_t match_digit8(uint32_t d) {
+  uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const uint32_t bit = (d >> b) & 1u;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bit);
+    m &= bit ? bal : ~bal;
+  }
+  return m;
+}
+
+// Exclusive sum-scan over the first 256 threads of the CTA (value of threads >= 256 is ignored).
+// Every thread of the CTA must call it (contains __syncthreads). s_tot: 8 words of shared memory.
+__device__ __forceinline__ uint32_t scan256_excl(uint32_t v, uint32_t* s_tot) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (w < 8 && lane == 31) s_tot[w] = inc;
+  __syncthreads();
+  uint32_t base = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t t = s_tot[i];
+    if (i < w) base += t;
+  }
+  __syncthreads();
+  return base + inc - v;
+}
+
+// =====================================================================================================
+// k_prep_block — block contract front end.  Replaces std::reverse + "*end = 0" of
+// BWTransform::doTransform(BWTBlock&,freqs) (BWTransform.cpp:53-55) and the ++freqs[U[i]] loop of
+// divbwtf (divsufsort.c:506-512): text[i] = X[n-1-i], text[n] = 0 (+ zero padding), hist = byte counts.
+// One thread produces 4 text bytes (coalesced 32-bit stores; the reversed byte loads hit L1).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_prep_block(const uint8_t* __restrict__ X, uint32_t n,
+                                                    uint8_t* __restrict__ text, uint32_t padded_words,
+                                                    uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_hist[256];
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < padded_words; wi += gridDim.x * blockDim.x) {
+    const uint32_t o = wi * 4u;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t i = o + j;
+      if (i < n) {
+        const uint32_t ch = X[n - 1u - i];
+        packed |= ch << (8 * j);
+        atomicAdd(&s_hist[ch], 1u);
+      }
+    }
+    reinterpret_cast<uint32_t*>(text)[wi] = packed;
+  }
+  __syncthreads();
+  const uint32_t v = s_hist[threadIdx.x];
+  if (v) atomicAdd(&hist[threadIdx.x], v);
+}
+
+// k_hist_bytes — raw contract front end: hist of T[0..cnt) (the freqs of divbwtf, divsufsort.c:506-512).
+__global__ void __launch_bounds__(256) k_hist_bytes(const uint8_t* __restrict__ T, uint32_t cnt,
+                                                    uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_hist[256];
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
+    atomicAdd(&s_hist[T[i]], 1u);
+  __syncthreads();
+  const uint32_t v = s_hist[threadIdx.x];
+  if (v) atomicAdd(&hist[threadIdx.x], v);
+}
+
+// =====================================================================================================
+// k_pack_round0 — round-0 keys.  Position t of the key array holds suffix i = N-1-t (descending suffix
+// ids, see DESIGN.md §3.2: with a stable sort, suffixes whose c-character window runs past the end of
+// the text then precede every other suffix with an equal key, which is their correct order), so no code
+// point has to be reserved for the sentinel.  key = c dense b-bit codes, most significant = first char.
+// The digit histograms of ALL radix passes of the round are accumulated here (shared-memory atomics,
+// one global flush per CTA; persistent grid), so the sort never re-reads the keys to count.
+// Replaces the bucket counting of sort_typeBstar (divsufsort.c:62-74).
+// =====================================================================================================
+struct PackParams {
+  uint8_t lut[256];   // byte -> dense code
+  uint32_t bits;      // b
+  uint32_t chars;     // c  (c*b <= 8*sizeof(KeyT), c <= 64)
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__ text, uint32_t N,
+                                                     KeyT* __restrict__ keys, PackParams pp,
+                                                     uint32_t* __restrict__ hist, int npass, uint32_t ntiles) {
+  constexpr int BLOCK = 256, IPT = 8, TILE = BLOCK * IPT;
+  __shared__ uint8_t s_lut[256];
+  __shared__ uint8_t s_code[TILE + 64];
+  __shared__ uint32_t s_hist[8 * 256];
+  const int tid = threadIdx.x;
+  s_lut[tid] = pp.lut[tid];
+#pragma unroll
+  for (int p = 0; p < 8; ++p) s_hist[p * 256 + tid] = 0;
+  __syncthreads();
+  const uint32_t c = pp.chars, b = pp.bits;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t t0 = tile * (uint32_t)TILE;
+    const long long wlo = (long long)N - (long long)t0 - TILE;  // text index held in s_code[0]
+    for (int q = tid; q < TILE + 63; q += BLOCK) {
+      const long long g = wlo + q;
+      s_code[q] = (g >= 0 && g < (long long)N) ? s_lut[text[g]] : (uint8_t)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t u = k * BLOCK + tid;
+      const uint32_t t = t0 + u;
+      if (t < N) {
+        const int q0 = TILE - 1 - (int)u;
+        KeyT key = 0;
+        for (uint32_t j = 0; j < c; ++j) key = (KeyT)(key << b) | (KeyT)s_code[q0 + j];
+        keys[t] = key;
+        for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + (uint32_t)((key >> (8 * p)) & 0xFF)], 1u);
+      }
+    }
+    __syncthreads();
+  }
+  for (int p = 0; p < npass; ++p) {
+    const uint32_t v = s_hist[p * 256 + tid];
+    if (v) atomicAdd(&hist[p * 256 + tid], v);
+  }
+}
+
+// =====================================================================================================
+// k_build_keys — doubling round r >= 1.  Text-order scan of rank[]: both reads (rank[i], rank[i+h]) are
+// coalesced; only suffixes still in a non-singleton group emit a record.  key = rank[i] << lo_bits |
+// (rank[i+h] + 1), 0 in the low part when i+h is past the end (sorts first = "shorter suffix first").
+// Compaction is fused (warp ballots -> CTA offsets -> ONE global atomic per tile; record order is
+// irrelevant to the sort) and so are the digit histograms of every pass of this round.
+// Replaces "ISAd = ISA + depth" + tr_introsort's key access of trsort (trsort.c:327-552,563).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_build_keys(const uint32_t* __restrict__ rank, uint32_t N, uint32_t h,
+                                                    int lo_bits, unsigned long long* __restrict__ keys,
+                                                    uint32_t* __restrict__ idx, uint32_t* __restrict__ ctrl,
+                                                    uint32_t* __restrict__ hist, int npass, uint32_t ntiles) {
+  constexpr int BLOCK = 256, IPT = 8, TILE = BLOCK * IPT, WARPS = BLOCK / 32;
+  __shared__ uint32_t s_hist[8 * 256];
+  __shared__ uint32_t s_cnt[WARPS * IPT];
+  __shared__ uint32_t s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) s_hist[p * 256 + tid] = 0;
+  __syncthreads();
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t base_i = tile * (uint32_t)TILE;
+    unsigned long long key[IPT];
+    uint32_t livemask = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t i = base_i + k * BLOCK + tid;
+      key[k] = 0;
+      bool live = false;
+      if (i < N) {
+        const uint32_t r = rank[i];
+        if (!(r & RANK_DONE)) {
+          live = true;
+          const uint32_t r2 = (h < N - i) ? ((rank[i + h] & RANK_MASK) + 1u) : 0u;
+          key[k] = ((unsigned long long)r << lo_bits) | (unsigned long long)r2;
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, live);
+      if (live) livemask |= 1u << k;
+      if (lane == 0) s_cnt[warp * IPT + k] = __popc(bal);
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the WARPS*IPT (=64) per-(warp,k) counts, 2 per lane
+      const uint32_t a = s_cnt[2 * lane], bb = s_cnt[2 * lane + 1];
+      uint32_t inc = a + bb;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const uint32_t excl = inc - (a + bb);
+      s_cnt[2 * lane] = excl;
+      s_cnt[2 * lane + 1] = excl + a;
+      if (lane == 31) s_base = inc ? atomicAdd(&ctrl[CTR_CURSOR], inc) : 0u;
+    }
+    __syncthreads();
+    const uint32_t gbase = s_base;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const bool live = (livemask >> k) & 1u;
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, live);
+      if (live) {
+        const uint32_t pos = gbase + s_cnt[warp * IPT + k] + __popc(bal & lanemask_lt());
+        keys[pos] = key[k];
+        idx[pos] = base_i + k * BLOCK + tid;
+        for (int p = 0; p < npass; ++p)
+          atomicAdd(&s_hist[p * 256 + (uint32_t)((key[k] >> (8 * p)) & 0xFF)], 1u);
+      }
+    }
+    __syncthreads();
+  }
+  for (int p = 0; p < npass; ++p) {
+    const uint32_t v = s_hist[p * 256 + tid];
+    if (v) atomicAdd(&hist[p * 256 + tid], v);
+  }
+}
+static_assert((256 / 32) * 8 == 64, "k_build_keys scans exactly 64 (warp,k) counters with one warp");
+
+// =====================================================================================================
+// k_radix_pass — one 8-bit digit pass of the LSD radix sort over (key, suffix id) records, single sweep:
+//   * dynamic tile ids (atomic ticket) so a tile only ever waits on tiles that already started,
+//   * warp-striped coalesced loads, keys/values held in registers,
+//   * per-warp digit ranking with 8 ballots per item (match_digit8) into per-warp shared histograms,
+//   * per-digit decoupled look-back across tiles (status word = 2 flag bits + 30-bit count; the data
+//     travels inside the flag word, so no fence is needed), with a spin watchdog instead of a hang,
+//   * records are staged in shared memory in sorted order and written out with consecutive threads
+//     writing consecutive addresses of a bin's run (coalesced scatter).
+// HBM traffic per record: read key+id, write key+id — the algorithmic minimum for an out-of-place pass.
+// IOTA: first pass of round 0 — suffix ids are implied by position (id = iota_top - position), not read.
+// Stable, which the round-0 sentinel handling relies on.
+// Replaces sssort/trsort's comparison sorting (sssort.c:310,654,746; trsort.c:327).
+// =====================================================================================================
+template <typename KeyT, int BLOCK, int IPT>
+struct RadixPassSmem {
+  static constexpr int TILE = BLOCK * IPT;
+  static constexpr int WARPS = BLOCK / 32;
+  static constexpr size_t bytes = sizeof(KeyT) * TILE + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 32);
+};
+
+template <typename KeyT, int BLOCK, int IPT, bool IOTA>
+__global__ void __launch_bounds__(BLOCK) k_radix_pass(const KeyT* __restrict__ keys_in,
+                                                      const uint32_t* __restrict__ vals_in,
+                                                      KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                      uint32_t n, uint32_t shift,
+                                                      const uint32_t* __restrict__ ghist,
+                                                      uint32_t* __restrict__ status, uint32_t* __restrict__ ctrl,
+                                                      uint32_t ctr_slot, uint32_t iota_top) {
+  static_assert(BLOCK >= 256 && BLOCK % 32 == 0, "BLOCK must cover the 256 digit bins");
+  constexpr int TILE = BLOCK * IPT, WARPS = BLOCK / 32;
+  static_assert(TILE <= 65536, "local positions are kept as uint16");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* s_whist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(KeyT) * TILE);
+  uint32_t* s_binbase = s_whist + WARPS * 256;
+  uint32_t* s_texcl = s_binbase + 256;
+  uint32_t* s_misc = s_texcl + 256;  // [0] tile id, [8..15] scan scratch
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_misc[0] = atomicAdd(&ctrl[ctr_slot], 1u);
+  for (int i = tid; i < WARPS * 256; i += BLOCK) s_whist[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_misc[0];
+  const uint32_t tile_base = tile * (uint32_t)TILE;
+  if (tile_base >= n) return;  // cannot happen with grid == ceil(n / TILE); defensive
+  const uint32_t valid = (n - tile_base < (uint32_t)TILE) ? (n - tile_base) : (uint32_t)TILE;
+
+  // ---- load (warp-striped)
+  KeyT key[IPT];
+  uint32_t val[IPT];
+  const uint32_t first = tile_base + warp * (32 * IPT) + lane;
+  if (valid == (uint32_t)TILE) {
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) key[k] = keys_in[first + 32 * k];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) val[k] = IOTA ? (iota_top - (first + 32 * k)) : vals_in[first + 32 * k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t g = first + 32 * k;
+      key[k] = (g < n) ? keys_in[g] : (KeyT)~(KeyT)0;  // pads: digit 255, last in index order
+      val[k] = (g < n) ? (IOTA ? (iota_top - g) : vals_in[g]) : 0u;
+    }
+  }
+
+  // ---- rank inside the warp
+  uint16_t lpos[IPT];
+  uint32_t* my_hist = s_whist + warp * 256;
+  const uint32_t lt = lanemask_lt();
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
+    const uint32_t m = match_digit8(d);
+    const int leader = __ffs(m) - 1;
+    uint32_t old = 0;
+    if (lane == leader) {
+      old = my_hist[d];
+      my_hist[d] = old + __popc(m);
+    }
+    old = __shfl_sync(0xFFFFFFFFu, old, leader);
+    lpos[k] = (uint16_t)(old + __popc(m & lt));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per-digit: exclusive scan over warps, tile count
+  uint32_t cnt = 0;
+  if (tid < 256) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      const uint32_t t = s_whist[w * 256 + tid];
+      s_whist[w * 256 + tid] = run;
+      run += t;
+    }
+    cnt = run;
+  }
+  const uint32_t texcl = scan256_excl(cnt, s_misc + 8);
+  const uint32_t gcount = (tid < 256) ? ghist[tid] : 0u;
+  const uint32_t gexcl = scan256_excl(gcount, s_misc + 8);
+
+  // ---- decoupled look-back, one digit per thread
+  if (tid < 256) {
+    uint32_t pub = cnt;
+    if (tid == 255) pub -= ((uint32_t)TILE - valid);  // pads are not records
+    uint32_t* my_status = status + (size_t)tile * 256u + tid;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      st_volatile_u32(my_status, LB_PREFIX | pub);
+    } else {
+      st_volatile_u32(my_status, LB_AGG | pub);
+      uint32_t t = tile - 1;
+      uint32_t spins = 0;
+      while (true) {
+        const uint32_t v = ld_volatile_u32(status + (size_t)t * 256u + tid);
+        if (v & LB_PREFIX) {
+          excl += v & LB_VALUE;
+          break;
+        } else if (v & LB_AGG) {
+          excl += v & LB_VALUE;
+          if (t == 0) break;  // unreachable: tile 0 publishes PREFIX
+          --t;
+        } else if (++spins > LB_SPIN_LIMIT) {
+          atomicExch(&ctrl[CTR_ERR], 1u);
+          break;
+        } else {
+          __nanosleep(40);
+        }
+      }
+      st_volatile_u32(my_status, LB_PREFIX | ((excl + pub) & LB_VALUE));
+    }
+    s_texcl[tid] = texcl;
+    s_binbase[tid] = gexcl + excl - texcl;  // + local position = global position (mod 2^32)
+  }
+  __syncthreads();
+
+  // ---- stage keys in sorted order, then coalesced scatter
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
+    const uint32_t p = s_texcl[d] + my_hist[d] + lpos[k];
+    lpos[k] = (uint16_t)p;
+    s_keys[p] = key[k];
+  }
+  __syncthreads();
+  uint32_t gpos[IPT];
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t p = tid + k * BLOCK;
+    const KeyT kk = s_keys[p];
+    const uint32_t d = (uint32_t)(kk >> shift) & 0xFFu;
+    gpos[k] = s_binbase[d] + p;
+    if (p < valid) keys_out[gpos[k]] = kk;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) s_vals[lpos[k]] = val[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t p = tid + k * BLOCK;
+    if (p < valid) vals_out[gpos[k]] = s_vals[p];
+  }
+}
+
+// =====================================================================================================
+// k_rerank — segmented re-ranking after a sort round.  Over the sorted records j = 0..m-1:
+//   headfull(j): the full key differs from its predecessor's (ROUND0: or the predecessor's window ran past
+//                the end of the text — such a suffix is unique and precedes its equal-key neighbours);
+//   headhi(j)  : the old group (high key part) changes (ROUND0: only j = 0).
+//   HF(j), HH(j) = position of the last headfull / headhi at or before j  (two max-scans: thread-local,
+//                  warp shuffles, CTA, and a single 64-bit decoupled look-back word across tiles);
+//   new rank   = old_rank + HF(j) - HH(j)   (ROUND0: HF(j));   singleton = headfull(j) && headfull(j+1).
+// rank[idx[j]] is scattered only when it changes or becomes final.  The count of records left in
+// non-singleton groups goes to ctrl[CTR_LIVE]; no compacted list is written — k_build_keys re-derives
+// liveness from the RANK_DONE bit in text order.
+// Replaces the rank assignment of sort_typeBstar (divsufsort.c:147-158) and tr_partition / tr_copy
+// bookkeeping (trsort.c:220-323), negative-run skipping (trsort.c:563-585).
+// =====================================================================================================
+struct RerankParams {
+  uint32_t m;             // records
+  uint32_t short_thresh;  // ROUND0: suffix ids >= this have a window running past the text end
+  int lo_bits;            // width of the low key part (rounds >= 1)
+};
+
+template <typename KeyT, bool ROUND0>
+__global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx,
+                                                uint32_t* __restrict__ rank, RerankParams rp,
+                                                unsigned long long* __restrict__ tstate,
+                                                uint32_t* __restrict__ ctrl) {
+  constexpr int BLOCK = 256, IPT = 8, TILE = BLOCK * IPT, WARPS = BLOCK / 32;
+  __shared__ KeyT s_lastkey[BLOCK];
+  __shared__ uint32_t s_lastshort[BLOCK];
+  __shared__ uint32_t s_firsthead[BLOCK + 1];
+  __shared__ uint32_t s_wf[WARPS], s_wh[WARPS];
+  __shared__ uint32_t s_tile, s_cf, s_ch, s_live;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    s_tile = atomicAdd(&ctrl[CTR_RERANK], 1u);
+    s_live = 0;
+  }
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t m = rp.m;
+  const uint32_t tile_base = tile * (uint32_t)TILE;
+  if (tile_base >= m) return;
+  const uint32_t j0 = tile_base + tid * IPT;
+
+  KeyT key[IPT];
+  uint32_t id[IPT];
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t j = j0 + k;
+    key[k] = (j < m) ? keys[j] : (KeyT)0;
+    id[k] = (j < m) ? idx[j] : 0u;
+  }
+  // hand the last key (and its "short" flag) of every thread to its right neighbour
+  s_lastkey[tid] = key[IPT - 1];
+  if (ROUND0) s_lastshort[tid] = (j0 + IPT - 1 < m && id[IPT - 1] >= rp.short_thresh) ? 1u : 0u;
+  __syncthreads();
+  KeyT prevkey;
+  uint32_t prevshort = 0;
+  bool has_prev = true;
+  if (tid > 0) {
+    prevkey = s_lastkey[tid - 1];
+    if (ROUND0) prevshort = s_lastshort[tid - 1];
+  } else if (tile_base > 0) {
+    prevkey = keys[tile_base - 1];
+    if (ROUND0) prevshort = (idx[tile_base - 1] >= rp.short_thresh) ? 1u : 0u;
+  } else {
+    prevkey = 0;
+    has_prev = false;
+  }
+
+  // thread-local flags and running maxima (positions stored +1, 0 = none)
+  uint32_t headfull = 0, headhi = 0;  // bit k
+  uint32_t lf[IPT], lh[IPT];
+  uint32_t runf = 0, runh = 0;
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t j = j0 + k;
+    bool hf, hh;
+    if (j >= m) {
+      hf = hh = true;  // terminator for singleton detection; never written
+    } else if (k == 0 && !has_prev) {
+      hf = hh = true;
+    } else {
+      const KeyT pk = (k == 0) ? prevkey : key[k - 1];
+      const uint32_t ps = ROUND0 ? ((k == 0) ? prevshort : ((id[k - 1] >= rp.short_thresh) ? 1u : 0u)) : 0u;
+      hf = (key[k] != pk) || (ps != 0);
+      hh = ROUND0 ? false : ((key[k] >> rp.lo_bits) != (pk >> rp.lo_bits));
+    }
+    if (hf) { headfull |= 1u << k; runf = j + 1; }
+    if (hh) { headhi |= 1u << k; runh = j + 1; }
+    lf[k] = runf;
+    lh[k] = runh;
+  }
+  s_firsthead[tid] = headfull & 1u;
+  // CTA-wide exclusive max-scan of (runf, runh)
+  uint32_t incf = runf, inch = runh;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t tf = __shfl_up_sync(0xFFFFFFFFu, incf, o);
+    const uint32_t th = __shfl_up_sync(0xFFFFFFFFu, inch, o);
+    if (lane >= o) { incf = max(incf, tf); inch = max(inch, th); }
+  }
+  if (lane == 31) { s_wf[warp] = incf; s_wh[warp] = inch; }
+  uint32_t exf = __shfl_up_sync(0xFFFFFFFFu, incf, 1);
+  uint32_t exh = __shfl_up_sync(0xFFFFFFFFu, inch, 1);
+  if (lane == 0) { exf = 0; exh = 0; }
+  __syncthreads();
+  uint32_t aggf = 0, aggh = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) {
+    const uint32_t tf = s_wf[w], th = s_wh[w];
+    if (w < warp) { exf = max(exf, tf); exh = max(exh, th); }
+    aggf = max(aggf, tf);
+    aggh = max(aggh, th);
+  }
+  // tile look-back (one 64-bit word per tile: flag[63:62] | HH+1 [61:31] | HF+1 [30:0])
+  if (tid == 0) {
+    uint32_t cf = 0, ch = 0;
+    const unsigned long long mine = ((unsigned long long)aggh << 31) | (unsigned long long)aggf;
+    if (tile == 0) {
+      st_volatile_u64(tstate, (2ull << 62) | mine);
+    } else {
+      st_volatile_u64(tstate + tile, (1ull << 62) | mine);
+      uint32_t t = tile - 1, spins = 0;
+      while (true) {
+        const unsigned long long v = ld_volatile_u64(tstate + t);
+        const uint32_t flag = (uint32_t)(v >> 62);
+        if (flag) {
+          cf = max(cf, (uint32_t)(v & 0x7FFFFFFFull));
+          ch = max(ch, (uint32_t)((v >> 31) & 0x7FFFFFFFull));
+          if (flag == 2u || t == 0) break;
+          --t;
+        } else if (++spins > LB_SPIN_LIMIT) {
+          atomicExch(&ctrl[CTR_ERR], 2u);
+          break;
+        } else {
+          __nanosleep(40);
+        }
+      }
+      st_volatile_u64(tstate + tile, (2ull << 62) | ((unsigned long long)max(ch, aggh) << 31) |
+                                         (unsigned long long)max(cf, aggf));
+    }
+    s_cf = cf;
+    s_ch = ch;
+    // head flag of the first record of the next tile (for the singleton test of my last record)
+    uint32_t nh = 1u;
+    const uint32_t jn = tile_base + TILE;
+    if (jn < m) {
+      const KeyT nk = keys[jn];
+      const KeyT lk = s_lastkey[BLOCK - 1];
+      const uint32_t ls = ROUND0 ? s_lastshort[BLOCK - 1] : 0u;
+      nh = (nk != lk || ls) ? 1u : 0u;
+    }
+    s_firsthead[BLOCK] = nh;
+  }
+  __syncthreads();
+  exf = max(exf, s_cf);
+  exh = max(exh, s_ch);
+  const uint32_t nexthead_thread = s_firsthead[tid + 1];
+
+  uint32_t live = 0;
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t j = j0 + k;
+    if (j < m) {
+      const uint32_t HF = max(lf[k], exf) - 1u;  // >= 0: record 0 is always a head
+      const bool hf = (headfull >> k) & 1u;
+      const bool nh = (k == IPT - 1) ? (nexthead_thread != 0) : ((headfull >> (k + 1)) & 1u);
+      const bool single = hf && nh;
+      uint32_t nr;
+      bool changed;
+      if (ROUND0) {
+        nr = HF;
+        changed = true;
+      } else {
+        const uint32_t HH = max(lh[k], exh) - 1u;
+        nr = (uint32_t)(key[k] >> rp.lo_bits) + (HF - HH);
+        changed = (HF != HH);
+      }
+      if (single) nr |= RANK_DONE; else ++live;
+      if (changed || single) rank[id[k]] = nr;
+    }
+  }
+  // CTA reduce of live -> one global atomic
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) live += __shfl_down_sync(0xFFFFFFFFu, live, o);
+  if (lane == 0 && live) atomicAdd(&s_live, live);
+  __syncthreads();
+  if (tid == 0 && s_live) atomicAdd(&ctrl[CTR_LIVE], s_live);
+}
+
+// =====================================================================================================
+// k_final — fused BWT emission + primary index + LFpowers + hole fill.  rank[] is now the inverse suffix
+// array, so in text order (coalesced reads of rank and text):  L[rank[i]] = T[i-1].
+//   block contract (BWTransform.cpp:52-64): out[0..n) = L[0..n) with out[pidx] = L[N-1] (hole fill);
+//   raw contract   (divsufsort.c:506-512) : U[r] = L[r] for r != pidx, U[pidx] = T[pidx] ("untouched").
+//   LFpowers[0] = pidx = rank[0]; LFpowers[j] = rank[N - j*(N/nLF)]     (divsufsort.c:337-338,350,381,390,500).
+// The byte scatter lands in an L2-resident output block (<= 126 MB L2 for blocks up to ~100 MiB).
+// Replaces construct_BWT / construct_BWT_orig (divsufsort.c:259-404) and the copy loop (:506-512).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_final(const uint32_t* __restrict__ rank, const uint8_t* __restrict__ text,
+                                               uint32_t N, uint8_t* __restrict__ out, int block_mode,
+                                               uint32_t* __restrict__ LF, uint32_t nLF) {
+  const uint32_t pidx = rank[0] & RANK_MASK;
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid < nLF) {
+    const uint32_t x = N / nLF;
+    LF[gid] = (gid == 0) ? pidx : (rank[N - gid * x] & RANK_MASK);
+  }
+  for (uint32_t i = gid; i < N; i += gridDim.x * blockDim.x) {
+    const uint32_t r = rank[i] & RANK_MASK;
+    if (i == 0) {
+      if (!block_mode) out[pidx] = text[pidx];
+    } else {
+      const uint8_t ch = text[i - 1];
+      if (block_mode && r == N - 1) out[pidx] = ch;  // hole fill: begin[LF[0]] = *end
+      else out[r] = ch;
+    }
+  }
+}
+
+}  // namespace bwtc_b200
