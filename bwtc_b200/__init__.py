@@ -143,8 +143,8 @@ def num_starting_points(block_bytes: int, starts: int) -> int:
 class CudaContext:
     """One in-flight block: a CUDA stream + device scratch (bwtc_cuda_ctx)."""
 
-    def __init__(self, max_block_bytes: int, device: int = 0):
-        self._lib = load_library()
+    def __init__(self, max_block_bytes: int, device: int = 0, lib_path: Optional[str] = None):
+        self._lib = load_library(lib_path)
         h = _vp()
         rc = self._lib.bwtc_cuda_ctx_create(ctypes.byref(h), device, max_block_bytes)
         if rc != 0:

@@ -140,8 +140,11 @@ void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* pr
     if (chars > cmax) chars = cmax;
     if (chars < 1) chars = 1;
   } else {
-    // an i.i.d. source of entropy H0 separates all but ~2^-6 of N suffixes after need/H0 characters;
-    // sources with memory (H_rate < H0) simply leave more suffixes live for the doubling rounds.
+    // An i.i.d. source of entropy H0 separates all but ~2^-6 of N suffixes after need/H0 characters.  If that
+    // fits a 32-bit key the round-0 sort moves 8-byte records in <= 4 passes (random bytes, DNA).  Otherwise
+    // the source has memory or a small alphabet relative to N (text, repeats): every extra character ordered
+    // in round 0 is far cheaper than a doubling round over the suffixes it would leave live (measured:
+    // profiles/r01_sweep_round0.md), so the 64-bit key is filled completely.
     const double need = std::log2((double)N + 1.0) + 6.0;
     double cn = std::ceil(need / (H0 > 1e-3 ? H0 : 1e-3));
     if (cn > 64) cn = 64;
@@ -153,9 +156,7 @@ void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* pr
       if (chars > cmax32) chars = cmax32;
     } else {
       keybytes = 8;
-      const uint32_t np = div_up((uint64_t)(c_need < cmax64 ? c_need : cmax64) * b, 8);
-      chars = (8 * np) / b;
-      if (chars > cmax64) chars = cmax64;
+      chars = cmax64;
     }
   }
   pl->sigma = sigma;
@@ -295,9 +296,18 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     present[c] = count[c] != 0;
     if (freqs) freqs[c] += ctx->h_hist()[c];
   }
-  const uint8_t last = block_mode ? (uint8_t)0 : h_in[N - 1];
-  present[last] = true;
-  count[last] += 1;
+  // Block contract: the appended 0x00 only enters the alphabet if the block itself contains 0x00.  Otherwise
+  // it is a true sentinel: it gets code 0 like the padding past the end, and the "window ran past the end"
+  // rule of the round-0 re-rank starts one position earlier — a 4-letter alphabet then packs
+  // into 2 bits per character instead of 3.
+  bool sentinel_outside_alphabet = false;
+  if (block_mode) {
+    if (!present[0]) sentinel_outside_alphabet = true;
+  } else {
+    const uint8_t last = h_in[N - 1];
+    present[last] = true;
+    count[last] += 1;
+  }
 
   Round0Plan pl;
   plan_round0(ctx, count, present, N, &pl);
@@ -346,7 +356,10 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   {
     RerankParams rp;
     rp.m = N;
-    rp.short_thresh = pl.chars > N ? 0u : N - pl.chars + 1u;
+    {
+      const uint32_t text_end = sentinel_outside_alphabet ? N - 1 : N;  // windows reaching text_end are unique
+      rp.short_thresh = pl.chars > text_end ? 0u : text_end - pl.chars + 1u;
+    }
     rp.lo_bits = 0;
     const uint32_t tiles = div_up(N, AUX_TILE);
     if (pl.keybytes == 4)
@@ -544,6 +557,14 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
     if (r2) { set_err(g_err, "%s", c->err); rc = BWTC_CUDA_ECUDA; }
   }
   if (rc) { ctx_free(c); return rc; }
+#ifdef BWTC_PROFILE_STAGES
+  {
+    unsigned long long* pbuf = nullptr;
+    cudaMalloc((void**)&pbuf, c->max_rs_tiles * 16 * 8);
+    cudaMemset(pbuf, 0, c->max_rs_tiles * 16 * 8);
+    cudaMemcpyToSymbol(g_prof_buf, &pbuf, sizeof(pbuf));
+  }
+#endif
   *out = c;
   return 0;
 }
@@ -598,6 +619,14 @@ int bwtc_cuda_debug_read(bwtc_cuda_ctx* ctx, int which, uint64_t offset_bytes, v
     case 5: src = reinterpret_cast<const uint8_t*>(ctx->d_idx[ctx->last_cur ^ 1]); break;
     case 6: src = reinterpret_cast<const uint8_t*>(ctx->d_zero); break;
     case 7: src = ctx->d_in; break;
+#ifdef BWTC_PROFILE_STAGES
+    case 8: {
+      unsigned long long* pbuf = nullptr;
+      CK(ctx, cudaMemcpyFromSymbol(&pbuf, g_prof_buf, sizeof(pbuf)));
+      src = reinterpret_cast<const uint8_t*>(pbuf);
+      break;
+    }
+#endif
     default: return BWTC_CUDA_EARG;
   }
   CK(ctx, cudaMemcpy(dst, src + offset_bytes, bytes, cudaMemcpyDeviceToHost));

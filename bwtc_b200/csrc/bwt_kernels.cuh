@@ -35,9 +35,25 @@ constexpr int CTR_WORDS = 32;
 // look-back status words of the radix pass: 2 flag bits + 30-bit count
 constexpr uint32_t LB_AGG = 0x40000000u, LB_PREFIX = 0x80000000u, LB_VALUE = 0x3FFFFFFFu;
 constexpr uint32_t LB_SPIN_LIMIT = 1u << 24;
+#ifndef BWTC_EARLY_PUBLISH
+#define BWTC_EARLY_PUBLISH 0
+#endif
+#ifndef BWTC_LB_LOAD
+#define BWTC_LB_LOAD 0
+#endif
+#ifndef BWTC_LB_BATCH
+#define BWTC_LB_BATCH 8
+#endif
+// Predecessor status words fetched per look-back round trip.  With T tiles in flight staggered by dt cycles
+// and a round trip of RT cycles the look-back settles at L = RT / (1 - RT / (dt * BATCH)): the batch must
+// satisfy dt * BATCH >> RT or the walk chases an ever longer chain of aggregate-only predecessors.
+constexpr int LB_BATCH = BWTC_LB_BATCH;
 
 #ifndef BWTC_RS_BLOCK
 #define BWTC_RS_BLOCK 256
+#endif
+#ifndef BWTC_RS_MINB
+#define BWTC_RS_MINB 3
 #endif
 #ifndef BWTC_RS_IPT64
 #define BWTC_RS_IPT64 16
@@ -59,6 +75,28 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+#if BWTC_LB_LOAD == 1
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#elif BWTC_LB_LOAD == 2
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#else
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#endif
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -70,6 +108,9 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
 
 // Lanes of the warp whose 8-bit digit equals mine (8 ballots; the multi-split primitive of the sort).
 __device__ __forceinline__ uint32_t match_digit8(uint32_t d) {
+#ifdef BWTC_USE_MATCH_ANY
+  return __match_any_sync(0xFFFFFFFFu, d);
+#endif
   uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
@@ -295,15 +336,22 @@ static_assert((256 / 32) * 8 == 64, "k_build_keys scans exactly 64 (warp,k) coun
 // Stable, which the round-0 sentinel handling relies on.
 // Replaces sssort/trsort's comparison sorting (sssort.c:310,654,746; trsort.c:327).
 // =====================================================================================================
+#ifdef BWTC_PROFILE_STAGES
+__device__ unsigned long long* g_prof_buf = nullptr;  // [tiles][16] SM-clock stamps (profiling builds only)
+#define BWTC_PROF(k) do { if (threadIdx.x == 0 && g_prof_buf) g_prof_buf[(size_t)tile * 16 + (k)] = clock64(); } while (0)
+#else
+#define BWTC_PROF(k) do { } while (0)
+#endif
+
 template <typename KeyT, int BLOCK, int IPT>
 struct RadixPassSmem {
   static constexpr int TILE = BLOCK * IPT;
   static constexpr int WARPS = BLOCK / 32;
-  static constexpr size_t bytes = sizeof(KeyT) * TILE + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 32);
+  static constexpr size_t bytes = sizeof(KeyT) * TILE + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 256 + 32);
 };
 
 template <typename KeyT, int BLOCK, int IPT, bool IOTA>
-__global__ void __launch_bounds__(BLOCK) k_radix_pass(const KeyT* __restrict__ keys_in,
+__global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* __restrict__ keys_in,
                                                       const uint32_t* __restrict__ vals_in,
                                                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                       uint32_t n, uint32_t shift,
@@ -319,13 +367,22 @@ __global__ void __launch_bounds__(BLOCK) k_radix_pass(const KeyT* __restrict__ k
   uint32_t* s_whist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(KeyT) * TILE);
   uint32_t* s_binbase = s_whist + WARPS * 256;
   uint32_t* s_texcl = s_binbase + 256;
-  uint32_t* s_misc = s_texcl + 256;  // [0] tile id, [8..15] scan scratch
+  uint32_t* s_tcnt = s_texcl + 256;
+  uint32_t* s_misc = s_tcnt + 256;  // [0] tile id, [8..15] scan scratch
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef BWTC_PROFILE_STAGES
+  const unsigned long long t_entry = clock64();
+#endif
   if (tid == 0) s_misc[0] = atomicAdd(&ctrl[ctr_slot], 1u);
   for (int i = tid; i < WARPS * 256; i += BLOCK) s_whist[i] = 0;
+  if (tid < 256) s_tcnt[tid] = 0;
   __syncthreads();
   const uint32_t tile = s_misc[0];
+#ifdef BWTC_PROFILE_STAGES
+  if (tid == 0 && g_prof_buf) g_prof_buf[(size_t)tile * 16 + 0] = t_entry;
+#endif
+  BWTC_PROF(1);
   const uint32_t tile_base = tile * (uint32_t)TILE;
   if (tile_base >= n) return;  // cannot happen with grid == ceil(n / TILE); defensive
   const uint32_t valid = (n - tile_base < (uint32_t)TILE) ? (n - tile_base) : (uint32_t)TILE;
@@ -348,6 +405,46 @@ __global__ void __launch_bounds__(BLOCK) k_radix_pass(const KeyT* __restrict__ k
     }
   }
 
+#ifdef BWTC_PROFILE_STAGES
+  {
+    KeyT acc = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) acc ^= key[k] ^ (KeyT)val[k];
+    if (acc == (KeyT)0x123456789ABCDEFull) s_misc[1] = 1;  // forces the loads to land before stamp 2
+    __syncthreads();
+    BWTC_PROF(2);
+  }
+#endif
+#if BWTC_EARLY_PUBLISH
+  // ---- count: digit histogram of the tile (shared atomics; one atomic per warp when its 32 digits agree,
+  // which is the common case for the high digits of low-entropy text).  Publishing the counts BEFORE the
+  // expensive ranking decouples the tile chain: by the time this tile looks back, its predecessors have
+  // long since published, so nobody waits on the slowest tile in flight.
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
+    const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, d, 0);
+    if (__all_sync(0xFFFFFFFFu, d == d0)) {
+      if (lane == 0) atomicAdd(&s_tcnt[d0], 32u);
+    } else {
+      atomicAdd(&s_tcnt[d], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t cnt = 0, pub = 0;
+  uint32_t* my_status = status + (size_t)tile * 256u + (tid & 255);
+  if (tid < 256) {
+    cnt = s_tcnt[tid];
+    pub = cnt;
+    if (tid == 255) pub -= ((uint32_t)TILE - valid);  // pads are not records
+    st_relaxed_u32(my_status, (tile == 0 ? LB_PREFIX : LB_AGG) | pub);
+  }
+  BWTC_PROF(3);
+
+#else
+  uint32_t cnt = 0, pub = 0;
+  uint32_t* my_status = status + (size_t)tile * 256u + (tid & 255);
+#endif
   // ---- rank inside the warp
   uint16_t lpos[IPT];
   uint32_t* my_hist = s_whist + warp * 256;
@@ -367,9 +464,9 @@ __global__ void __launch_bounds__(BLOCK) k_radix_pass(const KeyT* __restrict__ k
     __syncwarp();
   }
   __syncthreads();
+  BWTC_PROF(4);
 
-  // ---- per-digit: exclusive scan over warps, tile count
-  uint32_t cnt = 0;
+  // ---- per-digit: exclusive scan over warps; tile-local and global exclusive digit offsets
   if (tid < 256) {
     uint32_t run = 0;
 #pragma unroll
@@ -378,48 +475,20 @@ __global__ void __launch_bounds__(BLOCK) k_radix_pass(const KeyT* __restrict__ k
       s_whist[w * 256 + tid] = run;
       run += t;
     }
+#if !BWTC_EARLY_PUBLISH
     cnt = run;
+    pub = cnt;
+    if (tid == 255) pub -= ((uint32_t)TILE - valid);  // pads are not records
+    st_relaxed_u32(my_status, (tile == 0 ? LB_PREFIX : LB_AGG) | pub);
+#endif
   }
   const uint32_t texcl = scan256_excl(cnt, s_misc + 8);
   const uint32_t gcount = (tid < 256) ? ghist[tid] : 0u;
   const uint32_t gexcl = scan256_excl(gcount, s_misc + 8);
-
-  // ---- decoupled look-back, one digit per thread
-  if (tid < 256) {
-    uint32_t pub = cnt;
-    if (tid == 255) pub -= ((uint32_t)TILE - valid);  // pads are not records
-    uint32_t* my_status = status + (size_t)tile * 256u + tid;
-    uint32_t excl = 0;
-    if (tile == 0) {
-      st_volatile_u32(my_status, LB_PREFIX | pub);
-    } else {
-      st_volatile_u32(my_status, LB_AGG | pub);
-      uint32_t t = tile - 1;
-      uint32_t spins = 0;
-      while (true) {
-        const uint32_t v = ld_volatile_u32(status + (size_t)t * 256u + tid);
-        if (v & LB_PREFIX) {
-          excl += v & LB_VALUE;
-          break;
-        } else if (v & LB_AGG) {
-          excl += v & LB_VALUE;
-          if (t == 0) break;  // unreachable: tile 0 publishes PREFIX
-          --t;
-        } else if (++spins > LB_SPIN_LIMIT) {
-          atomicExch(&ctrl[CTR_ERR], 1u);
-          break;
-        } else {
-          __nanosleep(40);
-        }
-      }
-      st_volatile_u32(my_status, LB_PREFIX | ((excl + pub) & LB_VALUE));
-    }
-    s_texcl[tid] = texcl;
-    s_binbase[tid] = gexcl + excl - texcl;  // + local position = global position (mod 2^32)
-  }
+  if (tid < 256) s_texcl[tid] = texcl;
   __syncthreads();
 
-  // ---- stage keys in sorted order, then coalesced scatter
+  // ---- ... stage keys in sorted order (needs tile-local offsets only) while predecessors publish
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
     const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
@@ -427,7 +496,68 @@ __global__ void __launch_bounds__(BLOCK) k_radix_pass(const KeyT* __restrict__ k
     lpos[k] = (uint16_t)p;
     s_keys[p] = key[k];
   }
+
+  BWTC_PROF(5);
+  // ---- decoupled look-back, one digit per thread, LB_BATCH predecessor words in flight per round trip
+  if (tid < 256) {
+    uint32_t excl = 0;
+    if (tile != 0) {
+      long long t = (long long)tile - 1;
+      uint32_t spins = 0;
+      bool done = false;
+#ifdef BWTC_PROFILE_STAGES
+      uint32_t prof_iters = 0;
+#endif
+      while (!done) {
+#ifdef BWTC_PROFILE_STAGES
+        ++prof_iters;
+#endif
+        uint32_t v[LB_BATCH];
+#pragma unroll
+        for (int i = 0; i < LB_BATCH; ++i) {
+          const long long ti = t - i;
+          v[i] = (ti >= 0) ? ld_relaxed_u32(status + (size_t)ti * 256u + tid) : LB_PREFIX;
+        }
+        int consumed = 0;
+        bool stop = false;
+#pragma unroll
+        for (int i = 0; i < LB_BATCH; ++i) {
+          if (!stop) {
+            if (v[i] & LB_PREFIX) {
+              excl += v[i] & LB_VALUE;
+              done = true;
+              stop = true;
+            } else if (v[i] & LB_AGG) {
+              excl += v[i] & LB_VALUE;
+              ++consumed;
+            } else {
+              stop = true;
+            }
+          }
+        }
+        t -= consumed;
+        if (!done && consumed == 0) {
+          if (++spins > LB_SPIN_LIMIT) {
+            atomicExch(&ctrl[CTR_ERR], 1u);
+            break;
+          }
+          __nanosleep(20);
+        }
+      }
+      st_relaxed_u32(my_status, LB_PREFIX | ((excl + pub) & LB_VALUE));
+#ifdef BWTC_PROFILE_STAGES
+      if (tid == 0 && g_prof_buf) {
+        g_prof_buf[(size_t)tile * 16 + 9] = prof_iters;
+        g_prof_buf[(size_t)tile * 16 + 10] = spins;
+        g_prof_buf[(size_t)tile * 16 + 11] = clock64();
+        g_prof_buf[(size_t)tile * 16 + 12] = (unsigned long long)((long long)tile - 1 - t);
+      }
+#endif
+    }
+    s_binbase[tid] = gexcl + excl - texcl;  // + local position = global position (mod 2^32)
+  }
   __syncthreads();
+  BWTC_PROF(6);
   uint32_t gpos[IPT];
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
@@ -438,6 +568,7 @@ __global__ void __launch_bounds__(BLOCK) k_radix_pass(const KeyT* __restrict__ k
     if (p < valid) keys_out[gpos[k]] = kk;
   }
   __syncthreads();
+  BWTC_PROF(7);
 #pragma unroll
   for (int k = 0; k < IPT; ++k) s_vals[lpos[k]] = val[k];
   __syncthreads();
@@ -446,6 +577,7 @@ __global__ void __launch_bounds__(BLOCK) k_radix_pass(const KeyT* __restrict__ k
     const uint32_t p = tid + k * BLOCK;
     if (p < valid) vals_out[gpos[k]] = s_vals[p];
   }
+  BWTC_PROF(8);
 }
 
 // =====================================================================================================
@@ -493,11 +625,36 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
 
   KeyT key[IPT];
   uint32_t id[IPT];
+  if (tile_base + TILE <= m) {  // full tile: 128-bit loads (buffers are 256-byte aligned, j0 % 8 == 0)
+    if (sizeof(KeyT) == 8) {
+      const ulonglong2* pk = reinterpret_cast<const ulonglong2*>(keys + j0);
 #pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    const uint32_t j = j0 + k;
-    key[k] = (j < m) ? keys[j] : (KeyT)0;
-    id[k] = (j < m) ? idx[j] : 0u;
+      for (int q = 0; q < IPT / 2; ++q) {
+        const ulonglong2 v = pk[q];
+        key[2 * q] = (KeyT)v.x;
+        key[2 * q + 1] = (KeyT)v.y;
+      }
+    } else {
+      const uint4* pk = reinterpret_cast<const uint4*>(keys + j0);
+#pragma unroll
+      for (int q = 0; q < IPT / 4; ++q) {
+        const uint4 v = pk[q];
+        key[4 * q] = (KeyT)v.x; key[4 * q + 1] = (KeyT)v.y; key[4 * q + 2] = (KeyT)v.z; key[4 * q + 3] = (KeyT)v.w;
+      }
+    }
+    const uint4* pi = reinterpret_cast<const uint4*>(idx + j0);
+#pragma unroll
+    for (int q = 0; q < IPT / 4; ++q) {
+      const uint4 v = pi[q];
+      id[4 * q] = v.x; id[4 * q + 1] = v.y; id[4 * q + 2] = v.z; id[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t j = j0 + k;
+      key[k] = (j < m) ? keys[j] : (KeyT)0;
+      id[k] = (j < m) ? idx[j] : 0u;
+    }
   }
   // hand the last key (and its "short" flag) of every thread to its right neighbour
   s_lastkey[tid] = key[IPT - 1];
@@ -562,45 +719,62 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
     aggf = max(aggf, tf);
     aggh = max(aggh, th);
   }
-  // tile look-back (one 64-bit word per tile: flag[63:62] | HH+1 [61:31] | HF+1 [30:0])
-  if (tid == 0) {
+  // tile look-back (one 64-bit word per tile: flag[63:62] | HH+1 [61:31] | HF+1 [30:0]); warp 0 inspects 32
+  // predecessor tiles per round trip
+  if (warp == 0) {
     uint32_t cf = 0, ch = 0;
     const unsigned long long mine = ((unsigned long long)aggh << 31) | (unsigned long long)aggf;
     if (tile == 0) {
-      st_volatile_u64(tstate, (2ull << 62) | mine);
+      if (lane == 0) st_relaxed_u64(tstate, (2ull << 62) | mine);
     } else {
-      st_volatile_u64(tstate + tile, (1ull << 62) | mine);
-      uint32_t t = tile - 1, spins = 0;
+      if (lane == 0) st_relaxed_u64(tstate + tile, (1ull << 62) | mine);
+      long long base = (long long)tile - 1;
+      uint32_t spins = 0;
       while (true) {
-        const unsigned long long v = ld_volatile_u64(tstate + t);
-        const uint32_t flag = (uint32_t)(v >> 62);
-        if (flag) {
-          cf = max(cf, (uint32_t)(v & 0x7FFFFFFFull));
-          ch = max(ch, (uint32_t)((v >> 31) & 0x7FFFFFFFull));
-          if (flag == 2u || t == 0) break;
-          --t;
-        } else if (++spins > LB_SPIN_LIMIT) {
-          atomicExch(&ctrl[CTR_ERR], 2u);
-          break;
-        } else {
-          __nanosleep(40);
+        const long long t = base - lane;
+        unsigned long long v = (t >= 0) ? ld_relaxed_u64(tstate + t) : (2ull << 62);
+        while ((v >> 62) == 0ull) {
+          if (++spins > LB_SPIN_LIMIT) {
+            atomicExch(&ctrl[CTR_ERR], 2u);
+            v = 2ull << 62;
+            break;
+          }
+          __nanosleep(20);
+          v = ld_relaxed_u64(tstate + t);
         }
+        const uint32_t pref = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2ull);
+        const int firstp = __ffs(pref) - 1;  // nearest predecessor holding an inclusive prefix
+        const bool use = (firstp < 0) || (lane <= firstp);
+        uint32_t f = use ? (uint32_t)(v & 0x7FFFFFFFull) : 0u;
+        uint32_t hh = use ? (uint32_t)((v >> 31) & 0x7FFFFFFFull) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          f = max(f, __shfl_xor_sync(0xFFFFFFFFu, f, o));
+          hh = max(hh, __shfl_xor_sync(0xFFFFFFFFu, hh, o));
+        }
+        cf = max(cf, f);
+        ch = max(ch, hh);
+        if (firstp >= 0) break;
+        base -= 32;
       }
-      st_volatile_u64(tstate + tile, (2ull << 62) | ((unsigned long long)max(ch, aggh) << 31) |
-                                         (unsigned long long)max(cf, aggf));
+      if (lane == 0)
+        st_relaxed_u64(tstate + tile, (2ull << 62) | ((unsigned long long)max(ch, aggh) << 31) |
+                                          (unsigned long long)max(cf, aggf));
     }
-    s_cf = cf;
-    s_ch = ch;
-    // head flag of the first record of the next tile (for the singleton test of my last record)
-    uint32_t nh = 1u;
-    const uint32_t jn = tile_base + TILE;
-    if (jn < m) {
-      const KeyT nk = keys[jn];
-      const KeyT lk = s_lastkey[BLOCK - 1];
-      const uint32_t ls = ROUND0 ? s_lastshort[BLOCK - 1] : 0u;
-      nh = (nk != lk || ls) ? 1u : 0u;
+    if (lane == 0) {
+      s_cf = cf;
+      s_ch = ch;
+      // head flag of the first record of the next tile (for the singleton test of my last record)
+      uint32_t nh = 1u;
+      const uint32_t jn = tile_base + TILE;
+      if (jn < m) {
+        const KeyT nk = keys[jn];
+        const KeyT lk = s_lastkey[BLOCK - 1];
+        const uint32_t ls = ROUND0 ? s_lastshort[BLOCK - 1] : 0u;
+        nh = (nk != lk || ls) ? 1u : 0u;
+      }
+      s_firsthead[BLOCK] = nh;
     }
-    s_firsthead[BLOCK] = nh;
   }
   __syncthreads();
   exf = max(exf, s_cf);

@@ -1,0 +1,221 @@
+"""GPU parity tests (the first gate): the CUDA path, called through the C-ABI, must be bit-exact with the oracle
+on the same seeded inputs, with the golden fixtures generated from the reference, and — at BASELINE.json's
+block sizes — satisfy size-independent properties (histogram preservation, reference-inverse round trip,
+pipeline == single-context)."""
+import numpy as np
+import pytest
+
+import bwtc_b200 as bw
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = bw.CudaContext(4 << 20)
+    yield c
+    c.close()
+
+
+def _gpu_block(ctx, x, starts, want_freqs=True):
+    blk = np.concatenate([x, np.array([0xAB], np.uint8)])
+    view = blk[:-1]
+    LF = np.zeros(bw.num_starting_points(x.size, starts), np.uint32)
+    fr = np.zeros(256, np.uint32) if want_freqs else None
+    pidx = ctx.bwt_block(view, LF, fr)
+    assert blk[-1] == 0xAB, "byte after the block must be preserved"
+    assert pidx == LF[0]
+    return view.copy(), LF, fr
+
+
+def test_golden_fixtures(ctx, golden):
+    for name, g in golden.items():
+        out, LF, fr = _gpu_block(ctx, g["in"], int(g["starts"][0]))
+        assert (out == g["out"]).all(), name
+        assert (LF == g["LF"]).all(), name
+        assert (fr == g["freqs"]).all(), name
+
+
+def test_block_contract_vs_oracle_random(ctx, oracle):
+    rng = np.random.default_rng(11)
+    sizes = [1, 2, 3, 4, 7, 8, 9, 31, 32, 33, 255, 256, 257, 258, 1000, 2047, 2048, 2049, 4095, 4096, 4097, 8191, 8192,
+             8193, 10000, 65535, 65536, 65537, 200000]
+    for n in sizes:
+        for sigma in (1, 2, 3, 4, 5, 64, 255, 256):
+            x = rng.integers(0, sigma, n).astype(np.uint8)
+            if sigma == 5:
+                x += 1  # no 0x00 in the block: the sentinel stays outside the alphabet
+            starts = int(rng.choice([1, 2, 7, 8, 256]))
+            want = oracle.block(x, starts)
+            got = _gpu_block(ctx, x, starts)
+            assert (got[0] == want[0]).all(), (n, sigma, starts)
+            assert (got[1] == want[1]).all(), (n, sigma, starts)
+            assert (got[2] == want[2]).all(), (n, sigma, starts)
+
+
+def test_freqs_are_incremented_not_overwritten(ctx):
+    x = np.frombuffer(b"abracadabra", np.uint8).copy()
+    LF = np.zeros(1, np.uint32)
+    fr = np.full(256, 5, np.uint32)
+    ctx.bwt_block(x.copy(), LF, fr)
+    assert fr[ord("a")] == 10 and fr[ord("z")] == 5
+
+
+def test_structured_inputs_vs_oracle(ctx, oracle):
+    rng = np.random.default_rng(12)
+    cases = {
+        "all zero": np.zeros(5000, np.uint8),
+        "all equal": np.full(70000, 0x41, np.uint8),
+        "ab*k": np.frombuffer(b"ab" * 30000, np.uint8).copy(),
+        "abc*k+z": np.frombuffer(b"abc" * 20000 + b"z", np.uint8).copy(),
+        "many zeros": np.where(rng.random(50000) < 0.9, 0, rng.integers(0, 256, 50000)).astype(np.uint8),
+        "zero tail": np.concatenate([rng.integers(1, 256, 3000), np.zeros(3000)]).astype(np.uint8),
+        "zero head": np.concatenate([np.zeros(3000), rng.integers(1, 256, 3000)]).astype(np.uint8),
+        "fibonacci": None,
+        "tiled+mut": None,
+        "descending": (255 - (np.arange(100000) % 256)).astype(np.uint8),
+    }
+    a, b = b"a", b"ab"
+    while len(b) < 100000:
+        a, b = b, b + a
+    cases["fibonacci"] = np.frombuffer(b[:100000], np.uint8).copy()
+    t = np.tile(rng.integers(0, 256, 777).astype(np.uint8), 200)
+    t[rng.integers(0, t.size, 100)] = 7
+    cases["tiled+mut"] = t
+    for name, x in cases.items():
+        for starts in (1, 8):
+            want = oracle.block(x, starts)
+            got = _gpu_block(ctx, x, starts)
+            assert (got[0] == want[0]).all() and (got[1] == want[1]).all() and (got[2] == want[2]).all(), (name, starts)
+
+
+@pytest.mark.parametrize("kind", ["markov", "dna", "repetitive", "random"])
+def test_input_families_1mib_vs_oracle(ctx, oracle, kind):
+    x = bw.generate(kind, 1 << 20, seed=21)
+    want = oracle.block(x, 8)
+    got = _gpu_block(ctx, x, 8)
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all() and (got[2] == want[2]).all()
+
+
+@pytest.mark.parametrize("force", [(0, 0), (1, 4), (3, 4), (2, 8), (5, 8), (64, 8)])
+def test_any_round0_key_shape_gives_identical_bytes(ctx, oracle, force):
+    """The round-0 key shape is a performance knob only."""
+    x = bw.generate("markov", 150001, seed=22)
+    want = oracle.block(x, 8)
+    ctx.set_round0(*force)
+    try:
+        got = _gpu_block(ctx, x, 8)
+    finally:
+        ctx.set_round0(0, 0)
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+
+
+def test_raw_contract_vs_oracle(ctx, oracle):
+    """doTransform(byte* begin, uint32 length, vector<uint32>& LF, freqs) on a caller-prepared buffer, as
+    test/InverseBwtTest.cpp:57-66 calls it; arbitrary last byte allowed (same semantics as divbwtf)."""
+    rng = np.random.default_rng(13)
+    for trial in range(60):
+        n = int(rng.integers(2, 20000))
+        sigma = int(rng.choice([1, 2, 4, 16, 256]))
+        T = rng.integers(0, sigma, n).astype(np.uint8)
+        if trial % 2 == 0:
+            T[-1] = 0  # the reference's own usage: reverse(text) + '\0'
+        nLF = int(rng.integers(1, min(n, 256) + 1))
+        rc, wbuf, wLF, wfr = oracle.raw(T, nLF)
+        U = T.copy()
+        LF = np.zeros(nLF, np.uint32)
+        fr = np.zeros(256, np.uint32)
+        pidx = ctx.divbwtf(U, U, LF, fr)
+        assert pidx == rc and (U == wbuf).all() and (LF == wLF).all() and (fr == wfr).all(), (trial, n, sigma, nLF)
+    # n <= 1 early-out (divsufsort.c:488-489): LFpowers untouched, returns n
+    U = np.array([9], np.uint8)
+    LF = np.array([77], np.uint32)
+    assert ctx.divbwtf(U, U, LF, None) == 1 and LF[0] == 77 and U[0] == 9
+
+
+def test_error_behaviour(ctx):
+    small = bw.CudaContext(1000)
+    with pytest.raises(bw.BwtcCudaError) as e:
+        small.bwt_block(np.zeros(2000, np.uint8), np.zeros(8, np.uint32), None)
+    assert e.value.code == -5
+    with pytest.raises(bw.BwtcCudaError) as e:  # nLF > N: x = N / nLF would be 0 (UB in the reference)
+        small.divbwtf(np.zeros(4, np.uint8), np.zeros(4, np.uint8), np.zeros(8, np.uint32), None)
+    assert e.value.code == -1
+    small.close()
+
+
+def test_manager_interface_matches_oracle(oracle):
+    """Reads like the reference's own use: BWTManager m(starts); m.initialize(c); m.doTransform(block, freqs)."""
+    x = bw.generate("markov", 300000, seed=23)
+    want = oracle.block(x, 8)
+    m = bw.BWTManager(8, max_block_bytes=x.size)
+    m.initialize("c")
+    data = x.copy()
+    block = bw.BWTBlock(data)
+    fr = np.zeros(256, np.uint32)
+    m.doTransform(block, fr)
+    assert block.isTransformed()
+    assert (data == want[0]).all() and (block.LFpowers() == want[1]).all() and (fr == want[2]).all()
+
+
+def test_pipeline_equals_single_context(oracle):
+    rng = np.random.default_rng(14)
+    sizes = [1, 300, 70000, 1 << 18, 123457, 1 << 18, 999, 1 << 17]
+    blocks = [bw.generate(["markov", "dna", "repetitive", "random"][i % 4], s, seed=100 + i) for i, s in enumerate(sizes)]
+    want = [oracle.block(b, 8) for b in blocks]
+    pipe = bw.Pipeline(1 << 18, depth=3)
+    work = [b.copy() for b in blocks]
+    LF, nLF, freqs, stats = pipe.run(work, starts=8)
+    for i, w in enumerate(want):
+        assert (work[i] == w[0]).all(), i
+        assert (LF[i, : nLF[i]] == w[1]).all(), i
+        assert (freqs[i] == w[2]).all(), i
+        assert stats[i]["n_suffixes"] == sizes[i] + 1
+    pipe.close()
+
+
+@pytest.mark.parametrize("kind,mib", [("markov", 32), ("dna", 64), ("repetitive", 16), ("random", 64)])
+def test_full_size_properties(reference, kind, mib):
+    """BASELINE.json block sizes: size-independent properties instead of the (slow) oracle —
+    byte histogram preserved, freqs == histogram, LFpowers in range and distinct, and the REFERENCE's own
+    inverse transform (MtlSaInverseBWT via InverseBWTransform::doTransform(BWTBlock&)) restores the block."""
+    n = mib << 20
+    x = bw.generate(kind, n, seed=31)
+    ctx = bw.CudaContext(n)
+    blk = x.copy()
+    LF = np.zeros(8, np.uint32)
+    fr = np.zeros(256, np.uint32)
+    pidx = ctx.bwt_block(blk, LF, fr)
+    st = ctx.stats()
+    ctx.close()
+    assert st["n_suffixes"] == n + 1 and st["live"][0] == n + 1
+    hist = np.bincount(x, minlength=256)
+    assert (np.bincount(blk, minlength=256) == hist).all()
+    assert (fr == hist).all()
+    assert pidx == LF[0] and (LF <= n).all() and len(set(LF.tolist())) == LF.size
+    back = reference.inverse_block(blk, LF)
+    assert (back == x).all()
+
+
+def test_256mib_random_block_properties():
+    """config 4: 256 MiB block (29-bit ranks, 8 doubling-key passes, ~8.3 GB of scratch)."""
+    n = 256 << 20
+    x = bw.generate("random", n, seed=32)
+    ctx = bw.CudaContext(n)
+    blk = x.copy()
+    LF = np.zeros(8, np.uint32)
+    fr = np.zeros(256, np.uint32)
+    ctx.bwt_block(blk, LF, fr)
+    ctx.close()
+    hist = np.bincount(x, minlength=256)
+    assert (fr == hist).all() and (np.bincount(blk, minlength=256) == hist).all()
+    # spot-check ranks: LFpowers[j] is the rank of suffix N - j*x of T' = reverse(X)+0; compare the order of the
+    # 8 sampled suffixes with a direct comparison of their first 64 bytes (random bytes differ long before that)
+    N = n + 1
+    T = np.concatenate([x[::-1], np.zeros(1, np.uint8)])
+    xs = N // 8
+    pos = [0] + [N - j * xs for j in range(1, 8)]
+    keys = [bytes(T[p: p + 64]) for p in pos]
+    order_by_rank = np.argsort(LF)
+    order_by_text = sorted(range(8), key=lambda i: keys[i])
+    assert list(order_by_rank) == order_by_text
