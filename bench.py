@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — forward-BWT throughput of the B200-native engine (BASELINE.json metric) + roofline + CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's own CPU path)
+
+A "step" is one pass of the hot path over one batch of synthetic input: BLOCKS_PER_STEP independent 32 MiB blocks
+of order-2 Markov text per GPU (BASELINE.json config 5 at one GPU's share), transformed through the batched
+pipeline (bwtc_cuda_pipeline_run, include/bwtc_cuda.h).
+  value : MB/s of input text, inputs and outputs resident in HBM, timed with CUDA events over all pipeline streams.
+  e2e   : the same metric through the host-buffer C-ABI call (pinned host in/out, H2D + D2H inside the timed region).
+  roofline : the dominant kernel (k_radix_pass): algorithmic bytes per launch / average launch duration, measured
+             live with CUDA events on the launching stream in a separate single-stream leg.
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref, divsufsort path) on the host cores, bounded sample.
+No oracle/ code is on the measured GPU path; oracle/_ref is executed only by the cpu_baseline / --impl reference legs.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK_BYTES = 32 << 20
+BLOCKS_PER_STEP = 16
+STARTS = 8
+KIND = "markov"
+WORKLOAD = ("order-2 Markov text (sigma 64, Dirichlet 0.05), 32 MiB blocks, %d blocks (512 MiB) per GPU per step, "
+            "8 starting points, block contract (BWTransform::doTransform(BWTBlock&, freqs))" % BLOCKS_PER_STEP)
+METRIC = "forward BWT MB/s (SA+BWT, 32 MiB blocks)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _gen_blocks(count, seed0, nbytes=BLOCK_BYTES, kind=KIND, out=None):
+    import bwtc_b200 as bw
+
+    bufs = out if out is not None else [np.empty(nbytes, np.uint8) for _ in range(count)]
+    with ThreadPoolExecutor(max_workers=min(count, os.cpu_count() or 1)) as ex:
+        list(ex.map(lambda i: bw.generate(kind, nbytes, seed=seed0 + i, out=bufs[i]), range(count)))
+    return bufs
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(pw)), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference
+class RefLib:
+    def __init__(self):
+        p = os.path.join(ROOT, "oracle", "_ref", "libbwtc_ref.so")
+        self.kind = "reference"
+        if not os.path.exists(p):
+            raise RuntimeError("oracle/_ref/libbwtc_ref.so missing (build with __graft_entry__.build() where "
+                               "/root/reference exists)")
+        self.lib = ctypes.CDLL(p)
+
+    def bwt_block(self, buf, n):
+        """BWTManager('d', 8 starting points).doTransform(block, freqs) — the reference's divsufsort path."""
+        LF = np.zeros(256, np.uint32)
+        k = ctypes.c_uint32(0)
+        fr = np.zeros(256, np.uint32)
+        self.lib.ref_bwt_block(ctypes.c_void_p(buf.ctypes.data), ctypes.c_uint(n), ctypes.c_uint(STARTS),
+                               ctypes.c_char(b"d"), ctypes.c_void_p(LF.ctypes.data), ctypes.byref(k),
+                               ctypes.c_void_p(fr.ctypes.data))
+
+
+def run_reference_threads(ref, blocks_src, cores):
+    """One worker thread per core with private buffers over independent blocks (ctypes drops the GIL).
+    Returns wall seconds for transforming len(blocks_src) blocks."""
+    work = [np.concatenate([b, np.zeros(1, np.uint8)]) for b in blocks_src]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(lambda w: ref.bwt_block(w, w.size - 1), work))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_sample(cores, blocks_per_core=1):
+    ref = RefLib()
+    nb = cores * blocks_per_core
+    blocks = _gen_blocks(nb, seed0=9000)
+    dt = run_reference_threads(ref, blocks, cores)
+    mbps = nb * BLOCK_BYTES / 1e6 / dt
+    return {"value": mbps, "unit": "MB/s", "cores": cores, "kind": "reference",
+            "per_core_mbps": mbps / cores,
+            "sample": "%d x 32 MiB Markov blocks (same generator as the GPU arm), one block per host thread, "
+                      "reference Divsufsorter via BWTManager('d'), 8 starting points, %.1f s wall" % (nb, dt)}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    ref = RefLib()
+    blocks = _gen_blocks(cores, seed0=9000)
+    for _ in range(args.warmup):
+        run_reference_threads(ref, blocks[: max(1, cores // 4)], cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += run_reference_threads(ref, blocks, cores)
+    mbps = args.steps * cores * BLOCK_BYTES / 1e6 / t
+    sample = ("each step = %d x 32 MiB Markov blocks, one per host thread (%d threads), reference Divsufsorter via "
+              "BWTManager('d'), 8 starting points" % (cores, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": mbps, "unit": "MB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 text / i32 suffix array",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": mbps, "unit": "MB/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": mbps, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import bwtc_b200 as bw
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nb, n = BLOCKS_PER_STEP, BLOCK_BYTES
+    # synthetic input: different blocks on every rank (weak scaling: per-GPU work fixed)
+    host_in = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(nb)]
+    host_out = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(nb)]
+    _gen_blocks(nb, seed0=1000 + 100 * rank, out=[t.numpy() for t in host_in])
+    dev_in = [t.to(dev) for t in host_in]
+    dev_out = [torch.empty_like(t) for t in dev_in]
+    torch.cuda.synchronize()
+
+    pipe = bw.Pipeline(n, depth=args.depth, device=local_rank)
+    sizes = [n] * nb
+    d_in = [t.data_ptr() for t in dev_in]
+    d_out = [t.data_ptr() for t in dev_out]
+    h_in = [t.data_ptr() for t in host_in]
+    h_out = [t.data_ptr() for t in host_out]
+
+    # ---- value: device-resident inputs/outputs, CUDA events over every pipeline stream
+    for _ in range(args.warmup):
+        pipe.run_ptrs(d_in, d_out, sizes, STARTS, on_device=True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches = 0
+    pipe.timing_begin()
+    t0 = time.perf_counter()
+    last_stats = None
+    for _ in range(args.steps):
+        LF, nLF, freqs, stats = pipe.run_ptrs(d_in, d_out, sizes, STARTS, on_device=True)
+        launches += sum(s["kernel_launches"] for s in stats)
+        last_stats = stats
+    ms_dev = pipe.timing_end()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # ---- e2e: host (pinned) buffers through the same C-ABI call, H2D + D2H inside the timed region
+    for _ in range(max(1, args.warmup // 2)):
+        pipe.run_ptrs(h_in, h_out, sizes, STARTS, on_device=False)
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        LFh, nLFh, freqsh, _ = pipe.run_ptrs(h_in, h_out, sizes, STARTS, on_device=False)
+    barrier()
+    e2e_s = time.perf_counter() - t1
+    # the two paths must agree (device result vs host result of the same blocks)
+    assert (LFh == LF).all() and (freqsh == freqs).all()
+    assert torch.equal(dev_out[0].cpu(), host_out[0]) and torch.equal(dev_out[-1].cpu(), host_out[-1])
+
+    # ---- max over ranks
+    times = torch.tensor([ms_dev, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
+    ltot = torch.tensor([launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ltot, op=dist.ReduceOp.SUM)
+    ms_dev_max, e2e_ms_max, wall_ms_max = [float(v) for v in times.tolist()]
+    total_bytes = world * args.steps * nb * n
+    value = total_bytes / 1e6 / (ms_dev_max / 1e3)
+    e2e_value = total_bytes / 1e6 / (e2e_ms_max / 1e3)
+
+    line = None
+    if rank == 0:
+        peak, peak_src = _peaks()
+        # ---- roofline leg: one context, one stream, every radix pass bracketed by CUDA events
+        ctx = bw.CudaContext(n, device=local_rank)
+        ctx.set_timing(1)
+        LF1 = np.zeros(STARTS, np.uint32)
+        sort_ms = sort_bytes = sort_launches = 0
+        gpu_ms = alg_bytes = 0
+        for i in range(min(nb, 4) + 1):
+            ctx.bwt_block_device(d_in[i % nb], d_out[i % nb], n, LF1, None)
+            if i == 0:
+                continue  # warm-up
+            st = ctx.stats()
+            sort_ms += st["sort_ms"]
+            sort_bytes += st["sort_bytes"]
+            sort_launches += st["sort_launches"]
+            gpu_ms += st["gpu_ms"]
+            alg_bytes += st["algorithmic_bytes"]
+        ctx.close()
+        achieved = sort_bytes / 1e9 / (sort_ms / 1e3)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_radix_pass_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        st0 = last_stats[0]
+        roofline = {"bound": "hbm", "kernel": "k_radix_pass (one 8-bit LSD digit pass over (key, suffix id) records)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": peak_src, "traffic": traffic,
+                    "bytes_per_launch": sort_bytes / max(sort_launches, 1),
+                    "avg_launch_ms": sort_ms / max(sort_launches, 1), "launches_timed": sort_launches,
+                    "share_of_block_gpu_time": sort_ms / gpu_ms,
+                    "whole_block": {"algorithmic_bytes_per_input_byte": alg_bytes / (4.0 * n) if nb >= 4 else None,
+                                    "achieved_gbs": alg_bytes / 1e9 / (gpu_ms / 1e3),
+                                    "frac_of_peak": alg_bytes / 1e9 / (gpu_ms / 1e3) / peak,
+                                    "frac_of_nominal_8000": alg_bytes / 1e9 / (gpu_ms / 1e3) / 8000.0,
+                                    "rounds": st0["rounds"], "live": st0["live"], "passes": st0["passes"],
+                                    "chars_round0": st0["chars_round0"], "key_bytes_round0": st0["key_bytes_round0"]}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = cpu_baseline_sample(os.cpu_count() or 1)
+            except Exception as e:  # noqa: BLE001
+                cpu = {"value": None, "unit": "MB/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+        line = {"metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8 text / u32 ranks / u64 sort keys (integer)",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "pipeline_depth": args.depth,
+                           "l2": "every step streams 512 MiB of fresh blocks per GPU through ~1 GiB of scratch per "
+                                 "in-flight block, far larger than the 126 MB L2 (no flush needed)",
+                           "parallelism": "independent blocks sharded by rank, no collective on the data path"},
+                "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": nb * n,
+                        "d2h_bytes_per_step": nb * (n + 4 * STARTS + 256 * 4)},
+                "gpu_launches": int(ltot.item()),
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "wall_ms_per_step": wall_ms_max / args.steps}
+    pipe.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--depth", type=int, default=3, help="in-flight blocks (contexts) per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
