@@ -1,0 +1,68 @@
+/* bwtc_b200/host/divsufsort_shim.cpp — link-time drop-in for the reference's C entry points.
+ *
+ * Defines divbwt / divbwtf with EXACTLY the reference's signatures (bwtransforms/divsufsort.h:86-94) on top
+ * of the C-ABI, so an unmodified bwtc build that links this object INSTEAD of bwtransforms/divsufsort.c,
+ * sssort.c and trsort.c runs its Divsufsorter path (bwtransforms/Divsufsorter.hpp:54-65) on the GPU with no
+ * source change at all (option A).  oracle/Makefile.cudaref builds exactly that as a parity
+ * check: the resulting .bwtc files must be byte-identical to the reference's.
+ *
+ * A = scratch suffix array of the reference; ignored (the engine owns its scratch).  A failure cannot be
+ * reported through Divsufsorter (it drops the return value), so it aborts loudly: no CPU fallback.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+
+#include "../../include/bwtc_cuda.h"
+
+namespace {
+std::mutex g_mu;
+bwtc_cuda_ctx* g_ctx = 0;
+uint32_t g_cap = 0;
+
+bwtc_cuda_ctx* ctx_for(uint32_t n) {
+  if (g_ctx && n <= g_cap) return g_ctx;
+  uint64_t want = n;
+  if (g_ctx) {
+    want = (uint64_t)g_cap * 2 > want ? (uint64_t)g_cap * 2 : want;
+    bwtc_cuda_ctx_destroy(g_ctx);
+    g_ctx = 0;
+  }
+  if (want < (1u << 20)) want = 1u << 20;
+  if (want > BWTC_CUDA_MAX_BLOCK) want = BWTC_CUDA_MAX_BLOCK;
+  const char* dev = getenv("BWTC_CUDA_DEVICE");
+  int rc = bwtc_cuda_ctx_create(&g_ctx, dev ? atoi(dev) : 0, (uint32_t)want);
+  if (rc != 0) {
+    fprintf(stderr, "bwtc_b200 divsufsort shim: cannot create CUDA context (%d): %s\n", rc, bwtc_cuda_global_error());
+    abort();
+  }
+  g_cap = (uint32_t)want;
+  return g_ctx;
+}
+}  // namespace
+
+extern "C" {
+
+/* saidx_t is int32_t, sauchar_t is uint8_t (divsufsort.h:41-60) */
+int32_t divbwtf(const uint8_t* T, uint8_t* U, int32_t* A, int32_t n, unsigned* LFpowers, unsigned nLFpowers,
+                unsigned freqs[256]) {
+  (void)A;
+  if (T == 0 || U == 0 || n < 0) return -1;           /* divsufsort.c:488 */
+  if (n <= 1) { if (n == 1) U[0] = T[0]; return n; }  /* divsufsort.c:489 */
+  std::lock_guard<std::mutex> lock(g_mu);
+  bwtc_cuda_ctx* c = ctx_for((uint32_t)n);
+  int64_t rc = bwtc_cuda_divbwtf(c, T, U, (uint32_t)n, LFpowers, nLFpowers, freqs);
+  if (rc < 0) {
+    fprintf(stderr, "bwtc_b200 divsufsort shim: GPU transform failed (%lld): %s\n", (long long)rc, bwtc_cuda_last_error(c));
+    abort();
+  }
+  return (int32_t)rc;
+}
+
+int32_t divbwt(const uint8_t* T, uint8_t* U, int32_t* A, int32_t n, unsigned* LFpowers, unsigned nLFpowers) {
+  return divbwtf(T, U, A, n, LFpowers, nLFpowers, 0);
+}
+
+const char* divsufsort_version(void) { return "bwtc_b200 CUDA drop-in for libdivsufsort 2.0.0 (bwtc-modified)"; }
+
+}  // extern "C"
