@@ -206,7 +206,12 @@ def main_gpu(args):
     # synthetic input: different blocks on every rank (weak scaling: per-GPU work fixed)
     host_in = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(nb)]
     host_out = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(nb)]
-    _gen_blocks(nb, seed0=1000 + 100 * rank, out=[t.numpy() for t in host_in])
+    # block i of the global stream -> rank i mod G (bwtc_b200/sharding.py); seeds follow the GLOBAL block index
+    from bwtc_b200 import sharding
+    mine = sharding.blocks_for_rank(nb * world, rank, world)
+    assert len(mine) == nb
+    with ThreadPoolExecutor(max_workers=min(nb, os.cpu_count() or 1)) as ex:
+        list(ex.map(lambda j: bw.generate(KIND, n, seed=1000 + mine[j], out=host_in[j].numpy()), range(nb)))
     dev_in = [t.to(dev) for t in host_in]
     dev_out = [torch.empty_like(t) for t in dev_in]
     torch.cuda.synchronize()
