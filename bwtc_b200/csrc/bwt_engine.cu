@@ -19,6 +19,9 @@ using namespace bwtc_b200;
 
 namespace {
 
+#ifndef BWTC_RS_PERSIST
+#define BWTC_RS_PERSIST 1
+#endif
 constexpr int RS_BLOCK = BWTC_RS_BLOCK;
 constexpr int RS_IPT64 = BWTC_RS_IPT64;
 constexpr int RS_IPT32 = BWTC_RS_IPT32;
@@ -68,7 +71,10 @@ struct bwtc_cuda_ctx {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   int timing_detail = 0;
+  int persist_ctas64 = 148, persist_ctas32 = 148;  // resident CTAs of k_radix_pass_persist
+  int use_persist = BWTC_RS_PERSIST;
   uint32_t force_chars = 0, force_keybytes = 0;
+  uint64_t rerank_window_bytes = 72ull << 20;  // rank-scatter window kept L2-resident (126 MB L2)
   uint32_t debug_max_rounds = 0;  // != 0: stop refining after this many rounds (results are then wrong on purpose)
   int last_cur = 0;               // sort buffer holding the last round's sorted records
   bwtc_cuda_stats stats;
@@ -97,6 +103,14 @@ template <typename KeyT, int IPT, bool IOTA>
 int set_pass_attr(bwtc_cuda_ctx* ctx) {
   CK(ctx, cudaFuncSetAttribute(k_radix_pass<KeyT, RS_BLOCK, IPT, IOTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)RadixPassSmem<KeyT, RS_BLOCK, IPT>::bytes));
+  CK(ctx, cudaFuncSetAttribute(k_radix_pass_persist<KeyT, RS_BLOCK, IPT, IOTA>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)RadixPersistSmem<KeyT, RS_BLOCK, IPT>::bytes));
+  int nb = 0;
+  CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_radix_pass_persist<KeyT, RS_BLOCK, IPT, IOTA>, RS_BLOCK,
+                                                        RadixPersistSmem<KeyT, RS_BLOCK, IPT>::bytes));
+  if (nb < 1) nb = 1;
+  if (sizeof(KeyT) == 8) ctx->persist_ctas64 = nb * ctx->sm_count; else ctx->persist_ctas32 = nb * ctx->sm_count;
   return 0;
 }
 
@@ -168,6 +182,15 @@ void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* pr
   pl->pp.chars = chars;
 }
 
+// Number of id windows the rank scatter of a round is split into (k_rerank RerankParams::win_lo/hi).
+uint32_t rerank_windows(const bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m) {
+  if ((uint64_t)m * 4 < (uint64_t)N) return 1;  // few scattered writes: a second read of the records costs more
+  uint64_t w = ((uint64_t)N * 4 + ctx->rerank_window_bytes - 1) / ctx->rerank_window_bytes;
+  if (w < 1) w = 1;
+  if (w > MAX_RERANK_WINDOWS) w = MAX_RERANK_WINDOWS;
+  return (uint32_t)w;
+}
+
 struct PassTimer {
   bwtc_cuda_ctx* ctx;
   size_t used = 0;
@@ -203,7 +226,19 @@ int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota
     KeyT* kout = static_cast<KeyT*>(ctx->d_keys[cur ^ 1]);
     uint32_t* status = ctx->d_status + (size_t)p * ctx->max_rs_tiles * 256u;
     if (pt->begin()) return BWTC_CUDA_ECUDA;
-    if (iota)
+    if (ctx->use_persist) {
+      const size_t psmem = RadixPersistSmem<KeyT, RS_BLOCK, IPT>::bytes;
+      const uint32_t resident = (uint32_t)(sizeof(KeyT) == 8 ? ctx->persist_ctas64 : ctx->persist_ctas32);
+      const uint32_t grid = tiles < resident ? tiles : resident;
+      if (iota)
+        k_radix_pass_persist<KeyT, RS_BLOCK, IPT, true><<<grid, RS_BLOCK, psmem, ctx->stream>>>(
+            kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
+            CTR_PASS0 + p, iota_top, tiles);
+      else
+        k_radix_pass_persist<KeyT, RS_BLOCK, IPT, false><<<grid, RS_BLOCK, psmem, ctx->stream>>>(
+            kin, ctx->d_idx[cur], kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
+            CTR_PASS0 + p, iota_top, tiles);
+    } else if (iota)
       k_radix_pass<KeyT, RS_BLOCK, IPT, true><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
           CTR_PASS0 + p, iota_top);
@@ -229,7 +264,7 @@ int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota
 
 int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t rs_tile, uint32_t pass_mask) {
   const uint32_t aux_tiles = div_up(m, AUX_TILE);
-  CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)aux_tiles * 8, ctx->stream));
+  CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)MAX_RERANK_WINDOWS * ctx->max_aux_tiles * 8, ctx->stream));
   const uint32_t tiles = div_up(m, rs_tile);
   for (int p = 0; p < MAX_PASSES; ++p)
     if ((pass_mask >> p) & 1u)
@@ -362,15 +397,22 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     }
     rp.lo_bits = 0;
     const uint32_t tiles = div_up(N, AUX_TILE);
-    if (pl.keybytes == 4)
-      k_rerank<uint32_t, true><<<tiles, 256, 0, st>>>(static_cast<const uint32_t*>(ctx->d_keys[cur]), ctx->d_idx[cur],
-                                                      ctx->d_rank, rp, ctx->d_tstate(), ctx->d_ctrl());
-    else
-      k_rerank<unsigned long long, true><<<tiles, 256, 0, st>>>(static_cast<const unsigned long long*>(ctx->d_keys[cur]),
-                                                                ctx->d_idx[cur], ctx->d_rank, rp, ctx->d_tstate(),
-                                                                ctx->d_ctrl());
-    CK(ctx, cudaGetLastError());
-    S.kernel_launches++;
+    const uint32_t nwin = rerank_windows(ctx, N, N);
+    const uint32_t extra_noop = getenv("BWTC_EXP_RERANK_NOOP") ? (uint32_t)atoi(getenv("BWTC_EXP_RERANK_NOOP")) : 0u;
+    for (uint32_t w = 0; w < nwin + extra_noop; ++w) {
+      rp.win_lo = w < nwin ? (uint32_t)((uint64_t)N * w / nwin) : 0u;
+      rp.win_hi = w < nwin ? (uint32_t)((uint64_t)N * (w + 1) / nwin) : 0u;  // w >= nwin: timing experiment, writes nothing
+      rp.ctr_slot = CTR_RERANK + w;
+      unsigned long long* ts = ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles;
+      if (pl.keybytes == 4)
+        k_rerank<uint32_t, true><<<tiles, 256, 0, st>>>(static_cast<const uint32_t*>(ctx->d_keys[cur]), ctx->d_idx[cur],
+                                                        ctx->d_rank, rp, ts, ctx->d_ctrl());
+      else
+        k_rerank<unsigned long long, true><<<tiles, 256, 0, st>>>(
+            static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp, ts, ctx->d_ctrl());
+      CK(ctx, cudaGetLastError());
+      S.kernel_launches++;
+    }
     S.algorithmic_bytes += (uint64_t)N * (pl.keybytes + 4) + (uint64_t)N * 4;
   }
   CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_WORDS * 4, cudaMemcpyDeviceToHost, st));
@@ -399,7 +441,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     if (zero_round_state(ctx, m, RS_TILE64, maskd)) return BWTC_CUDA_ECUDA;
     {
       const uint32_t btiles = div_up(N, AUX_TILE);
-      const int grid = (int)(btiles < (uint32_t)(ctx->sm_count * 4) ? btiles : (uint32_t)(ctx->sm_count * 4));
+      const int grid = (int)(btiles < (uint32_t)(ctx->sm_count * 8) ? btiles : (uint32_t)(ctx->sm_count * 8));
       k_build_keys<<<grid, 256, 0, st>>>(ctx->d_rank, N, (uint32_t)(h > 0xFFFFFFFFull ? 0xFFFFFFFFull : h), lo_bits,
                                          static_cast<unsigned long long*>(ctx->d_keys[0]), ctx->d_idx[0], ctx->d_ctrl(),
                                          ctx->d_hist(), (int)npassd, btiles);
@@ -415,11 +457,17 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       rp.m = m;
       rp.short_thresh = 0;
       rp.lo_bits = lo_bits;
-      k_rerank<unsigned long long, false><<<div_up(m, AUX_TILE), 256, 0, st>>>(
-          static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp, ctx->d_tstate(),
-          ctx->d_ctrl());
-      CK(ctx, cudaGetLastError());
-      S.kernel_launches++;
+      const uint32_t nwin = rerank_windows(ctx, N, m);
+      for (uint32_t w = 0; w < nwin; ++w) {
+        rp.win_lo = (uint32_t)((uint64_t)N * w / nwin);
+        rp.win_hi = (uint32_t)((uint64_t)N * (w + 1) / nwin);
+        rp.ctr_slot = CTR_RERANK + w;
+        k_rerank<unsigned long long, false><<<div_up(m, AUX_TILE), 256, 0, st>>>(
+            static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp,
+            ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl());
+        CK(ctx, cudaGetLastError());
+        S.kernel_launches++;
+      }
       S.algorithmic_bytes += (uint64_t)m * 12 + (uint64_t)m * 4;
     }
     CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_WORDS * 4, cudaMemcpyDeviceToHost, st));
@@ -443,9 +491,9 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
 
   // ---- final: fused BWT emission + pidx + LFpowers (+ hole fill)
   {
-    const uint32_t tiles = div_up(N, 256 * 8);
+    const uint32_t tiles = div_up(N, 256 * 16);
     const int grid = (int)(tiles < (uint32_t)(ctx->sm_count * 8) ? tiles : (uint32_t)(ctx->sm_count * 8));
-    k_final<<<grid > 0 ? grid : 1, 256, 0, st>>>(ctx->d_rank, d_text, N, d_dst, block_mode ? 1 : 0, ctx->d_LF, nLF);
+    k_final<<<grid > 0 ? grid : 1, 256, 0, st>>>(ctx->d_rank, d_text, N, d_dst, block_mode ? 1 : 0, ctx->d_LF, nLF, tiles);
     CK(ctx, cudaGetLastError());
     S.kernel_launches++;
     S.algorithmic_bytes += (uint64_t)N * 6;
@@ -506,6 +554,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (!c) { set_err(g_err, "out of host memory"); return BWTC_CUDA_EALLOC; }
   c->device = device;
   c->cap = max_block_bytes;
+  if (const char* e = getenv("BWTC_RERANK_WINDOW_MB")) { long v = atol(e); if (v > 0) c->rerank_window_bytes = (uint64_t)v << 20; }
   c->err[0] = 0;
   memset(&c->stats, 0, sizeof(c->stats));
   const size_t N = (size_t)max_block_bytes + 1;
@@ -531,12 +580,12 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_in, padded);
   ALLOC(c->d_text, padded);
   ALLOC(c->d_out, padded);
-  ALLOC(c->d_rank, (N + 1) * 4);
+  ALLOC(c->d_rank, (N + 64) * 4);
   ALLOC(c->d_keys[0], N * 8);
   ALLOC(c->d_keys[1], N * 8);
   ALLOC(c->d_idx[0], N * 4);
   ALLOC(c->d_idx[1], N * 4);
-  ALLOC(c->d_zero, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + c->max_aux_tiles * 8 + 64);
+  ALLOC(c->d_zero, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)MAX_RERANK_WINDOWS * c->max_aux_tiles * 8 + 64);
   ALLOC(c->d_status, (size_t)MAX_PASSES * c->max_rs_tiles * 1024u);
   ALLOC(c->d_LF, 256 * 4);
 #undef ALLOC

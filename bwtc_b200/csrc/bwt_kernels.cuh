@@ -26,7 +26,8 @@ constexpr uint32_t RANK_MASK = 0x7FFFFFFFu;
 
 // ---- control words (one uint32 array per context, zeroed by a memset at the start of every round)
 constexpr int CTR_PASS0 = 0;       // [0..15]  dynamic tile counters of the radix passes of this round
-constexpr int CTR_RERANK = 16;     // dynamic tile counter of k_rerank
+constexpr int CTR_RERANK = 20;     // [20..27] dynamic tile counters of the k_rerank window launches
+constexpr int MAX_RERANK_WINDOWS = 8;
 constexpr int CTR_CURSOR = 17;     // output cursor of k_build_keys (== number of live records emitted)
 constexpr int CTR_LIVE = 18;       // records still in non-singleton groups after k_rerank
 constexpr int CTR_ERR = 19;        // != 0: a look-back watchdog fired (engine returns BWTC_CUDA_EINTERNAL)
@@ -37,6 +38,9 @@ constexpr uint32_t LB_AGG = 0x40000000u, LB_PREFIX = 0x80000000u, LB_VALUE = 0x3
 constexpr uint32_t LB_SPIN_LIMIT = 1u << 24;
 #ifndef BWTC_EARLY_PUBLISH
 #define BWTC_EARLY_PUBLISH 0
+#endif
+#ifndef BWTC_EXP_ABLATE
+#define BWTC_EXP_ABLATE 0
 #endif
 #ifndef BWTC_LB_LOAD
 #define BWTC_LB_LOAD 0
@@ -258,69 +262,76 @@ __global__ void __launch_bounds__(256) k_build_keys(const uint32_t* __restrict__
                                                     uint32_t* __restrict__ hist, int npass, uint32_t ntiles) {
   constexpr int BLOCK = 256, IPT = 8, TILE = BLOCK * IPT, WARPS = BLOCK / 32;
   __shared__ uint32_t s_hist[8 * 256];
-  __shared__ uint32_t s_cnt[WARPS * IPT];
+  __shared__ uint32_t s_wtot[WARPS];
   __shared__ uint32_t s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int p = 0; p < 8; ++p) s_hist[p * 256 + tid] = 0;
   __syncthreads();
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint32_t base_i = tile * (uint32_t)TILE;
-    unsigned long long key[IPT];
+    // thread-blocked: 8 consecutive suffixes per thread, two 128-bit loads issued back to back (rank[] is
+    // 256-byte aligned and padded, so the vector loads of the last tile stay in bounds)
+    const uint32_t i0 = tile * (uint32_t)TILE + tid * IPT;
+    uint32_t r[IPT];
+    {
+      const uint4* pr = reinterpret_cast<const uint4*>(rank + i0);
+      uint4 a = make_uint4(RANK_DONE, RANK_DONE, RANK_DONE, RANK_DONE), b4 = a;
+      if (i0 < N) a = pr[0];
+      if (i0 + 4 < N) b4 = pr[1];
+      r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+      r[4] = b4.x; r[5] = b4.y; r[6] = b4.z; r[7] = b4.w;
+    }
     uint32_t livemask = 0;
 #pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-      const uint32_t i = base_i + k * BLOCK + tid;
-      key[k] = 0;
-      bool live = false;
-      if (i < N) {
-        const uint32_t r = rank[i];
-        if (!(r & RANK_DONE)) {
-          live = true;
-          const uint32_t r2 = (h < N - i) ? ((rank[i + h] & RANK_MASK) + 1u) : 0u;
-          key[k] = ((unsigned long long)r << lo_bits) | (unsigned long long)r2;
-        }
-      }
-      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, live);
-      if (live) livemask |= 1u << k;
-      if (lane == 0) s_cnt[warp * IPT + k] = __popc(bal);
-    }
-    __syncthreads();
-    if (warp == 0) {  // exclusive scan of the WARPS*IPT (=64) per-(warp,k) counts, 2 per lane
-      const uint32_t a = s_cnt[2 * lane], bb = s_cnt[2 * lane + 1];
-      uint32_t inc = a + bb;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      const uint32_t excl = inc - (a + bb);
-      s_cnt[2 * lane] = excl;
-      s_cnt[2 * lane + 1] = excl + a;
-      if (lane == 31) s_base = inc ? atomicAdd(&ctrl[CTR_CURSOR], inc) : 0u;
-    }
-    __syncthreads();
-    const uint32_t gbase = s_base;
+    for (int k = 0; k < IPT; ++k)
+      if (i0 + k < N && !(r[k] & RANK_DONE)) livemask |= 1u << k;
+    // second key halves: independent gathers, only for live suffixes
+    uint32_t r2[IPT];
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
-      const bool live = (livemask >> k) & 1u;
-      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, live);
-      if (live) {
-        const uint32_t pos = gbase + s_cnt[warp * IPT + k] + __popc(bal & lanemask_lt());
-        keys[pos] = key[k];
-        idx[pos] = base_i + k * BLOCK + tid;
-        for (int p = 0; p < npass; ++p)
-          atomicAdd(&s_hist[p * 256 + (uint32_t)((key[k] >> (8 * p)) & 0xFF)], 1u);
+      r2[k] = 0;
+      if ((livemask >> k) & 1u) {
+        const uint32_t i = i0 + k;
+        if (h < N - i) r2[k] = (rank[i + h] & RANK_MASK) + 1u;
       }
     }
+    // CTA-wide exclusive scan of the per-thread live counts -> one global atomic per tile
+    const uint32_t cnt = __popc(livemask);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wtot[warp] = inc;
     __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      const uint32_t t = s_wtot[w];
+      if (w < warp) woff += t;
+      total += t;
+    }
+    if (tid == 0) s_base = total ? atomicAdd(&ctrl[CTR_CURSOR], total) : 0u;
+    __syncthreads();
+    uint32_t pos = s_base + woff + inc - cnt;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      if ((livemask >> k) & 1u) {
+        const unsigned long long key = ((unsigned long long)r[k] << lo_bits) | (unsigned long long)r2[k];
+        keys[pos] = key;
+        idx[pos] = i0 + k;
+        ++pos;
+        for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + (uint32_t)((key >> (8 * p)) & 0xFF)], 1u);
+      }
+    }
   }
+  __syncthreads();
   for (int p = 0; p < npass; ++p) {
     const uint32_t v = s_hist[p * 256 + tid];
     if (v) atomicAdd(&hist[p * 256 + tid], v);
   }
 }
-static_assert((256 / 32) * 8 == 64, "k_build_keys scans exactly 64 (warp,k) counters with one warp");
 
 // =====================================================================================================
 // k_radix_pass — one 8-bit digit pass of the LSD radix sort over (key, suffix id) records, single sweep:
@@ -374,7 +385,11 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
 #ifdef BWTC_PROFILE_STAGES
   const unsigned long long t_entry = clock64();
 #endif
+#ifdef BWTC_EXP_NOTICKET
+  if (tid == 0) s_misc[0] = blockIdx.x;
+#else
   if (tid == 0) s_misc[0] = atomicAdd(&ctrl[ctr_slot], 1u);
+#endif
   for (int i = tid; i < WARPS * 256; i += BLOCK) s_whist[i] = 0;
   if (tid < 256) s_tcnt[tid] = 0;
   __syncthreads();
@@ -452,7 +467,15 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
     const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
+#if BWTC_EXP_ABLATE == 2 || BWTC_EXP_ABLATE == 4
+    lpos[k] = (uint16_t)(lane + 32 * k);
+    continue;
+#endif
+#if BWTC_EXP_ABLATE == 1
+    const uint32_t m = 1u << lane;
+#else
     const uint32_t m = match_digit8(d);
+#endif
     const int leader = __ffs(m) - 1;
     uint32_t old = 0;
     if (lane == leader) {
@@ -501,7 +524,11 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
   // ---- decoupled look-back, one digit per thread, LB_BATCH predecessor words in flight per round trip
   if (tid < 256) {
     uint32_t excl = 0;
+#ifdef BWTC_EXP_NOLOOKBACK
+    if (false) {
+#else
     if (tile != 0) {
+#endif
       long long t = (long long)tile - 1;
       uint32_t spins = 0;
       bool done = false;
@@ -565,6 +592,11 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
     const KeyT kk = s_keys[p];
     const uint32_t d = (uint32_t)(kk >> shift) & 0xFFu;
     gpos[k] = s_binbase[d] + p;
+#if BWTC_EXP_ABLATE >= 3
+    gpos[k] = tile_base + p;  // timing-only: identity placement (perfectly coalesced) to isolate the scatter cost
+#elif BWTC_EXP_ABLATE
+    if (gpos[k] >= n) gpos[k] = p % n;  // timing-only builds produce garbage positions: keep them in range
+#endif
     if (p < valid) keys_out[gpos[k]] = kk;
   }
   __syncthreads();
@@ -578,6 +610,258 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
     if (p < valid) vals_out[gpos[k]] = s_vals[p];
   }
   BWTC_PROF(8);
+}
+
+// =====================================================================================================
+// k_radix_pass_persist — the same digit pass as k_radix_pass, restructured for memory-level parallelism:
+//   * persistent CTAs (grid = resident CTAs), tiles handed out by the same atomic ticket;
+//   * the NEXT tile's keys and ids are prefetched into shared memory with cp.async.bulk (TMA 1-D bulk copy,
+//     completion on an mbarrier) while the current tile is ranked, looked back and scattered, so every CTA
+//     keeps a full tile of loads in flight all the time (the non-persistent kernel only has loads in flight
+//     during ~12% of a CTA's life, which caps it near 3 TB/s by Little's law);
+//   * two shared buffers per CTA: the buffer a tile arrived in is reused to stage that tile in sorted order
+//     (keys and ids side by side, so one scatter loop writes both), then becomes the prefetch target of the
+//     tile after next.
+// Ranking, publication, look-back and the output format are identical to k_radix_pass.
+// =====================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename KeyT, int BLOCK, int IPT>
+struct RadixPersistSmem {
+  static constexpr int TILE = BLOCK * IPT;
+  static constexpr int WARPS = BLOCK / 32;
+  static constexpr size_t buf_bytes = (sizeof(KeyT) + 4) * (size_t)TILE;
+  static constexpr size_t bytes = 2 * buf_bytes + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 32) + 2 * 8 + 128;
+};
+
+template <typename KeyT, int BLOCK, int IPT, bool IOTA>
+__global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass_persist(
+    const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, uint32_t n, uint32_t shift, const uint32_t* __restrict__ ghist,
+    uint32_t* __restrict__ status, uint32_t* __restrict__ ctrl, uint32_t ctr_slot, uint32_t iota_top, uint32_t ntiles) {
+  static_assert(BLOCK >= 256 && BLOCK % 32 == 0, "BLOCK must cover the 256 digit bins");
+  constexpr int TILE = BLOCK * IPT, WARPS = BLOCK / 32;
+  static_assert(TILE <= 65536, "local positions are kept as uint16");
+  constexpr size_t BUF = RadixPersistSmem<KeyT, BLOCK, IPT>::buf_bytes;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sbase = smem_raw;
+  uint32_t* s_whist = reinterpret_cast<uint32_t*>(sbase + 2 * BUF);
+  uint32_t* s_binbase = s_whist + WARPS * 256;
+  uint32_t* s_texcl = s_binbase + 256;
+  uint32_t* s_misc = s_texcl + 256;  // [0] current tile, [1] next tile, [8..15] scan scratch
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_misc + 32);  // 2 mbarriers
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = lanemask_lt();
+  uint32_t* my_hist = s_whist + warp * 256;
+  constexpr uint32_t KBYTES = (uint32_t)(sizeof(KeyT) * TILE), VBYTES = (uint32_t)(4 * TILE);
+
+  // global digit offsets are the same for every tile of this pass
+  const uint32_t gcount = (tid < 256) ? ghist[tid] : 0u;
+  const uint32_t gexcl = scan256_excl(gcount, s_misc + 8);
+
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t t0 = atomicAdd(&ctrl[ctr_slot], 1u);
+    s_misc[0] = t0;
+    if (t0 < ntiles && (t0 + 1) * (uint32_t)TILE <= n) {  // full tile: bulk prefetch into buffer 0
+      mbar_expect_tx(&s_bar[0], KBYTES + (IOTA ? 0u : VBYTES));
+      bulk_g2s(sbase, keys_in + (size_t)t0 * TILE, KBYTES, &s_bar[0]);
+      if (!IOTA) bulk_g2s(sbase + KBYTES, vals_in + (size_t)t0 * TILE, VBYTES, &s_bar[0]);
+    }
+    s_misc[1] = atomicAdd(&ctrl[ctr_slot], 1u);
+  }
+  __syncthreads();
+
+  uint32_t phase_bits = 0u;  // bit b = parity the next wait on buffer b expects
+  for (uint32_t it = 0;; ++it) {
+    const uint32_t b = it & 1u;
+    const uint32_t tile = s_misc[0];
+    const uint32_t tnext = s_misc[1];
+    if (tile >= ntiles) break;
+    unsigned char* bufc = sbase + (size_t)b * BUF;         // current tile: arrival buffer, then sorted staging
+    unsigned char* bufn = sbase + (size_t)(b ^ 1u) * BUF;  // prefetch target
+    const uint32_t tile_base = tile * (uint32_t)TILE;
+    const uint32_t valid = (n - tile_base < (uint32_t)TILE) ? (n - tile_base) : (uint32_t)TILE;
+    const bool full = (valid == (uint32_t)TILE);
+    __syncthreads();  // everyone has read s_misc[0..1]; previous iteration's scatter reads of bufn are done
+    if (tid == 0) {
+      if (tnext < ntiles && (tnext + 1) * (uint32_t)TILE <= n) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes to bufn precede the async write
+        mbar_expect_tx(&s_bar[b ^ 1u], KBYTES + (IOTA ? 0u : VBYTES));
+        bulk_g2s(bufn, keys_in + (size_t)tnext * TILE, KBYTES, &s_bar[b ^ 1u]);
+        if (!IOTA) bulk_g2s(bufn + KBYTES, vals_in + (size_t)tnext * TILE, VBYTES, &s_bar[b ^ 1u]);
+      }
+      s_misc[0] = tnext;                                  // becomes "current" at the next iteration
+      s_misc[1] = atomicAdd(&ctrl[ctr_slot], 1u);         // ticket two tiles ahead, latency hidden
+    }
+    for (int i = tid; i < WARPS * 256; i += BLOCK) s_whist[i] = 0;
+
+    // ---- current tile -> registers (warp-striped)
+    KeyT key[IPT];
+    uint32_t val[IPT];
+    const uint32_t lfirst = warp * (32 * IPT) + lane;
+    if (full) {
+      mbar_wait(&s_bar[b], (phase_bits >> b) & 1u);
+      phase_bits ^= 1u << b;
+      const KeyT* sk = reinterpret_cast<const KeyT*>(bufc);
+      const uint32_t* sv = reinterpret_cast<const uint32_t*>(bufc + KBYTES);
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) key[k] = sk[lfirst + 32 * k];
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) val[k] = IOTA ? (iota_top - (tile_base + lfirst + 32 * k)) : sv[lfirst + 32 * k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        const uint32_t g = tile_base + lfirst + 32 * k;
+        key[k] = (g < n) ? keys_in[g] : (KeyT)~(KeyT)0;  // pads: digit 255, last in index order
+        val[k] = (g < n) ? (IOTA ? (iota_top - g) : vals_in[g]) : 0u;
+      }
+    }
+    __syncthreads();  // bufc fully consumed (it is the staging buffer from here on); s_whist zeroed
+
+    // ---- rank inside the warp
+    uint16_t lpos[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
+      const uint32_t m = match_digit8(d);
+      const int leader = __ffs(m) - 1;
+      uint32_t old = 0;
+      if (lane == leader) {
+        old = my_hist[d];
+        my_hist[d] = old + __popc(m);
+      }
+      old = __shfl_sync(0xFFFFFFFFu, old, leader);
+      lpos[k] = (uint16_t)(old + __popc(m & lt));
+      __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per-digit scan over warps, publish the tile's digit counts
+    uint32_t cnt = 0, pub = 0;
+    uint32_t* my_status = status + (size_t)tile * 256u + (tid & 255);
+    if (tid < 256) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) {
+        const uint32_t t = s_whist[w * 256 + tid];
+        s_whist[w * 256 + tid] = run;
+        run += t;
+      }
+      cnt = run;
+      pub = cnt;
+      if (tid == 255) pub -= ((uint32_t)TILE - valid);  // pads are not records
+      st_relaxed_u32(my_status, (tile == 0 ? LB_PREFIX : LB_AGG) | pub);
+    }
+    const uint32_t texcl = scan256_excl(cnt, s_misc + 8);
+    if (tid < 256) s_texcl[tid] = texcl;
+    __syncthreads();
+
+    // ---- stage keys AND ids in sorted order into the arrival buffer
+    {
+      KeyT* sk = reinterpret_cast<KeyT*>(bufc);
+      uint32_t* sv = reinterpret_cast<uint32_t*>(bufc + KBYTES);
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
+        const uint32_t p = s_texcl[d] + my_hist[d] + lpos[k];
+        sk[p] = key[k];
+        sv[p] = val[k];
+      }
+    }
+
+    // ---- decoupled look-back, one digit per thread
+    if (tid < 256) {
+      uint32_t excl = 0;
+      if (tile != 0) {
+        long long t = (long long)tile - 1;
+        uint32_t spins = 0;
+        bool done = false;
+        while (!done) {
+          uint32_t v[LB_BATCH];
+#pragma unroll
+          for (int i = 0; i < LB_BATCH; ++i) {
+            const long long ti = t - i;
+            v[i] = (ti >= 0) ? ld_relaxed_u32(status + (size_t)ti * 256u + tid) : LB_PREFIX;
+          }
+          int consumed = 0;
+          bool stop = false;
+#pragma unroll
+          for (int i = 0; i < LB_BATCH; ++i) {
+            if (!stop) {
+              if (v[i] & LB_PREFIX) {
+                excl += v[i] & LB_VALUE;
+                done = true;
+                stop = true;
+              } else if (v[i] & LB_AGG) {
+                excl += v[i] & LB_VALUE;
+                ++consumed;
+              } else {
+                stop = true;
+              }
+            }
+          }
+          t -= consumed;
+          if (!done && consumed == 0) {
+            if (++spins > LB_SPIN_LIMIT) {
+              atomicExch(&ctrl[CTR_ERR], 1u);
+              break;
+            }
+            __nanosleep(20);
+          }
+        }
+        st_relaxed_u32(my_status, LB_PREFIX | ((excl + pub) & LB_VALUE));
+      }
+      s_binbase[tid] = gexcl + excl - texcl;  // + local position = global position (mod 2^32)
+    }
+    __syncthreads();
+
+    // ---- coalesced scatter of keys and ids
+    {
+      const KeyT* sk = reinterpret_cast<const KeyT*>(bufc);
+      const uint32_t* sv = reinterpret_cast<const uint32_t*>(bufc + KBYTES);
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        const uint32_t p = tid + k * BLOCK;
+        const KeyT kk = sk[p];
+        const uint32_t vv = sv[p];
+        const uint32_t d = (uint32_t)(kk >> shift) & 0xFFu;
+        const uint32_t g = s_binbase[d] + p;
+        if (p < valid) {
+          keys_out[g] = kk;
+          vals_out[g] = vv;
+        }
+      }
+    }
+  }
 }
 
 // =====================================================================================================
@@ -598,6 +882,10 @@ struct RerankParams {
   uint32_t m;             // records
   uint32_t short_thresh;  // ROUND0: suffix ids >= this have a window running past the text end
   int lo_bits;            // width of the low key part (rounds >= 1)
+  uint32_t win_lo, win_hi;  // only suffix ids in [win_lo, win_hi) are written / counted by this launch: the rank
+                            // scatter of a big block is split into windows that stay L2-resident (random 4-byte
+                            // writes into a >L2 array cost a DRAM sector fill + write-back each)
+  uint32_t ctr_slot;        // ctrl word used as the dynamic tile counter of this launch
 };
 
 template <typename KeyT, bool ROUND0>
@@ -610,10 +898,10 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
   __shared__ uint32_t s_lastshort[BLOCK];
   __shared__ uint32_t s_firsthead[BLOCK + 1];
   __shared__ uint32_t s_wf[WARPS], s_wh[WARPS];
-  __shared__ uint32_t s_tile, s_cf, s_ch, s_live;
+  __shared__ uint32_t s_tile, s_cf, s_ch, s_live, s_firsth0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    s_tile = atomicAdd(&ctrl[CTR_RERANK], 1u);
+    s_tile = atomicAdd(&ctrl[rp.ctr_slot], 1u);
     s_live = 0;
   }
   __syncthreads();
@@ -630,7 +918,7 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
       const ulonglong2* pk = reinterpret_cast<const ulonglong2*>(keys + j0);
 #pragma unroll
       for (int q = 0; q < IPT / 2; ++q) {
-        const ulonglong2 v = pk[q];
+        const ulonglong2 v = __ldcs(pk + q);
         key[2 * q] = (KeyT)v.x;
         key[2 * q + 1] = (KeyT)v.y;
       }
@@ -638,14 +926,14 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
       const uint4* pk = reinterpret_cast<const uint4*>(keys + j0);
 #pragma unroll
       for (int q = 0; q < IPT / 4; ++q) {
-        const uint4 v = pk[q];
+        const uint4 v = __ldcs(pk + q);
         key[4 * q] = (KeyT)v.x; key[4 * q + 1] = (KeyT)v.y; key[4 * q + 2] = (KeyT)v.z; key[4 * q + 3] = (KeyT)v.w;
       }
     }
     const uint4* pi = reinterpret_cast<const uint4*>(idx + j0);
 #pragma unroll
     for (int q = 0; q < IPT / 4; ++q) {
-      const uint4 v = pi[q];
+      const uint4 v = __ldcs(pi + q);
       id[4 * q] = v.x; id[4 * q + 1] = v.y; id[4 * q + 2] = v.z; id[4 * q + 3] = v.w;
     }
   } else {
@@ -698,6 +986,7 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
     lh[k] = runh;
   }
   s_firsthead[tid] = headfull & 1u;
+  if (tid == 0) s_firsth0 = headhi & 1u;
   // CTA-wide exclusive max-scan of (runf, runh)
   uint32_t incf = runf, inch = runh;
 #pragma unroll
@@ -719,47 +1008,56 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
     aggf = max(aggf, tf);
     aggh = max(aggh, th);
   }
-  // tile look-back (one 64-bit word per tile: flag[63:62] | HH+1 [61:31] | HF+1 [30:0]); warp 0 inspects 32
-  // predecessor tiles per round trip
+  // Tile look-back.  One 64-bit word per tile, two independently flagged components:
+  //   [63:62] flagH | [61:32] HH+1 | [31:30] flagF | [29:0] HF+1      (flag 1 = "no head in this tile", 2 = final)
+  // A max-scan of positions has a property a sum-scan lacks: a tile that CONTAINS a head already knows its
+  // inclusive prefix (its own last head), so it publishes "final" at once and never waits for anybody.  Only
+  // a tile whose first record is not a head needs the carry — normally found in the tile right before it —
+  // and only a tile with no head at all (inside a group longer than a tile) forwards what it found.
   if (warp == 0) {
+    const bool first_is_f = (s_firsthead[0] != 0);          // thread 0's first record is a full-key head
+    const bool first_is_h = ROUND0 ? true : (s_firsth0 != 0);
+    const uint32_t pubf = aggf & 0x3FFFFFFFu, pubh = ROUND0 ? 1u : (aggh & 0x3FFFFFFFu);
+    const uint32_t flagf = pubf ? 2u : 1u, flagh = pubh ? 2u : 1u;
     uint32_t cf = 0, ch = 0;
-    const unsigned long long mine = ((unsigned long long)aggh << 31) | (unsigned long long)aggf;
-    if (tile == 0) {
-      if (lane == 0) st_relaxed_u64(tstate, (2ull << 62) | mine);
-    } else {
-      if (lane == 0) st_relaxed_u64(tstate + tile, (1ull << 62) | mine);
+    if (lane == 0)
+      st_relaxed_u64(tstate + tile, ((unsigned long long)flagh << 62) | ((unsigned long long)pubh << 32) |
+                                        ((unsigned long long)flagf << 30) | (unsigned long long)pubf);
+    bool needf = !first_is_f && tile > 0, needh = !first_is_h && tile > 0;
+    if (needf || needh) {
       long long base = (long long)tile - 1;
       uint32_t spins = 0;
-      while (true) {
+      while (needf || needh) {
         const long long t = base - lane;
-        unsigned long long v = (t >= 0) ? ld_relaxed_u64(tstate + t) : (2ull << 62);
-        while ((v >> 62) == 0ull) {
+        unsigned long long v = (t >= 0) ? ld_relaxed_u64(tstate + t) : ((2ull << 62) | (2ull << 30));  // before tile 0
+        while ((v >> 62) == 0ull) {                                             // not published yet
           if (++spins > LB_SPIN_LIMIT) {
             atomicExch(&ctrl[CTR_ERR], 2u);
-            v = 2ull << 62;
+            v = (2ull << 62) | (2ull << 30);
             break;
           }
           __nanosleep(20);
           v = ld_relaxed_u64(tstate + t);
         }
-        const uint32_t pref = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2ull);
-        const int firstp = __ffs(pref) - 1;  // nearest predecessor holding an inclusive prefix
-        const bool use = (firstp < 0) || (lane <= firstp);
-        uint32_t f = use ? (uint32_t)(v & 0x7FFFFFFFull) : 0u;
-        uint32_t hh = use ? (uint32_t)((v >> 31) & 0x7FFFFFFFull) : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          f = max(f, __shfl_xor_sync(0xFFFFFFFFu, f, o));
-          hh = max(hh, __shfl_xor_sync(0xFFFFFFFFu, hh, o));
+        if (needf) {
+          const uint32_t fin = __ballot_sync(0xFFFFFFFFu, ((v >> 30) & 3ull) == 2ull);
+          if (fin) {
+            cf = __shfl_sync(0xFFFFFFFFu, (uint32_t)(v & 0x3FFFFFFFull), __ffs(fin) - 1);
+            needf = false;
+          }
         }
-        cf = max(cf, f);
-        ch = max(ch, hh);
-        if (firstp >= 0) break;
+        if (needh) {
+          const uint32_t fin = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2ull);
+          if (fin) {
+            ch = __shfl_sync(0xFFFFFFFFu, (uint32_t)((v >> 32) & 0x3FFFFFFFull), __ffs(fin) - 1);
+            needh = false;
+          }
+        }
         base -= 32;
       }
-      if (lane == 0)
-        st_relaxed_u64(tstate + tile, (2ull << 62) | ((unsigned long long)max(ch, aggh) << 31) |
-                                          (unsigned long long)max(cf, aggf));
+      if (lane == 0 && (flagf == 1u || flagh == 1u))  // forward the carry for the component(s) I have no head for
+        st_relaxed_u64(tstate + tile, (2ull << 62) | ((unsigned long long)(flagh == 1u ? ch : pubh) << 32) |
+                                          (2ull << 30) | (unsigned long long)(flagf == 1u ? cf : pubf));
     }
     if (lane == 0) {
       s_cf = cf;
@@ -800,8 +1098,12 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
         nr = (uint32_t)(key[k] >> rp.lo_bits) + (HF - HH);
         changed = (HF != HH);
       }
-      if (single) nr |= RANK_DONE; else ++live;
-      if (changed || single) rank[id[k]] = nr;
+#if BWTC_EXP_ABLATE
+      id[k] %= m;  // timing-only builds carry garbage ids
+#endif
+      const bool in_win = (id[k] >= rp.win_lo) && (id[k] < rp.win_hi);
+      if (single) nr |= RANK_DONE; else if (in_win) ++live;
+      if (in_win && (changed || single)) rank[id[k]] = nr;
     }
   }
   // CTA reduce of live -> one global atomic
@@ -823,21 +1125,49 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
 // =====================================================================================================
 __global__ void __launch_bounds__(256) k_final(const uint32_t* __restrict__ rank, const uint8_t* __restrict__ text,
                                                uint32_t N, uint8_t* __restrict__ out, int block_mode,
-                                               uint32_t* __restrict__ LF, uint32_t nLF) {
+                                               uint32_t* __restrict__ LF, uint32_t nLF, uint32_t ntiles) {
+  constexpr int IPT = 16;
   const uint32_t pidx = rank[0] & RANK_MASK;
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid < nLF) {
     const uint32_t x = N / nLF;
     LF[gid] = (gid == 0) ? pidx : (rank[N - gid * x] & RANK_MASK);
   }
-  for (uint32_t i = gid; i < N; i += gridDim.x * blockDim.x) {
-    const uint32_t r = rank[i] & RANK_MASK;
-    if (i == 0) {
-      if (!block_mode) out[pidx] = text[pidx];
+  // 16 consecutive suffixes per thread: four 128-bit rank loads + 16 text bytes in flight per thread
+  for (uint32_t t = gid; t < ntiles * 256u; t += gridDim.x * blockDim.x) {
+    const uint32_t i0 = t * IPT;
+    if (i0 >= N) continue;
+    uint32_t r[IPT];
+    uint8_t ch[IPT];
+    if (i0 + IPT <= N) {
+      const uint4* pr = reinterpret_cast<const uint4*>(rank + i0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = pr[q];
+        r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) ch[k] = (i0 + k > 0) ? text[i0 + k - 1] : (uint8_t)0;
     } else {
-      const uint8_t ch = text[i - 1];
-      if (block_mode && r == N - 1) out[pidx] = ch;  // hole fill: begin[LF[0]] = *end
-      else out[r] = ch;
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        const uint32_t i = i0 + k;
+        r[k] = (i < N) ? rank[i] : 0u;
+        ch[k] = (i < N && i > 0) ? text[i - 1] : (uint8_t)0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t i = i0 + k;
+      if (i >= N) break;
+      const uint32_t rr = r[k] & RANK_MASK;
+      if (i == 0) {
+        if (!block_mode) out[pidx] = text[pidx];
+      } else if (block_mode && rr == N - 1) {
+        out[pidx] = ch[k];  // hole fill: begin[LF[0]] = *end
+      } else {
+        out[rr] = ch[k];
+      }
     }
   }
 }
