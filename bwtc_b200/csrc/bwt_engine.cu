@@ -346,6 +346,13 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
 
   Round0Plan pl;
   plan_round0(ctx, count, present, N, &pl);
+  EmitParams ep;
+  ep.text = d_text;
+  ep.out = d_dst;
+  ep.lastch = ctx->d_LF + 256;
+  ep.N = N;
+  ep.block_mode = block_mode ? 1 : 0;
+  CK(ctx, cudaMemsetAsync(ctx->d_LF + 256, 0, 4, st));
   S.sigma = pl.sigma;
   S.bits_per_char = pl.bits;
   S.chars_round0 = pl.chars;
@@ -406,10 +413,10 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       unsigned long long* ts = ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles;
       if (pl.keybytes == 4)
         k_rerank<uint32_t, true><<<tiles, 256, 0, st>>>(static_cast<const uint32_t*>(ctx->d_keys[cur]), ctx->d_idx[cur],
-                                                        ctx->d_rank, rp, ts, ctx->d_ctrl());
+                                                        ctx->d_rank, rp, ts, ctx->d_ctrl(), ep);
       else
         k_rerank<unsigned long long, true><<<tiles, 256, 0, st>>>(
-            static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp, ts, ctx->d_ctrl());
+            static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp, ts, ctx->d_ctrl(), ep);
       CK(ctx, cudaGetLastError());
       S.kernel_launches++;
     }
@@ -464,7 +471,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
         rp.ctr_slot = CTR_RERANK + w;
         k_rerank<unsigned long long, false><<<div_up(m, AUX_TILE), 256, 0, st>>>(
             static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp,
-            ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl());
+            ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl(), ep);
         CK(ctx, cudaGetLastError());
         S.kernel_launches++;
       }
@@ -491,12 +498,10 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
 
   // ---- final: fused BWT emission + pidx + LFpowers (+ hole fill)
   {
-    const uint32_t tiles = div_up(N, 256 * 16);
-    const int grid = (int)(tiles < (uint32_t)(ctx->sm_count * 8) ? tiles : (uint32_t)(ctx->sm_count * 8));
-    k_final<<<grid > 0 ? grid : 1, 256, 0, st>>>(ctx->d_rank, d_text, N, d_dst, block_mode ? 1 : 0, ctx->d_LF, nLF, tiles);
+    k_finish<<<1, 256, 0, st>>>(ctx->d_rank, d_text, N, d_dst, block_mode ? 1 : 0, ctx->d_LF, nLF, ctx->d_LF + 256);
     CK(ctx, cudaGetLastError());
     S.kernel_launches++;
-    S.algorithmic_bytes += (uint64_t)N * 6;
+    S.algorithmic_bytes += (uint64_t)N * 2;  // text gather + BWT byte, charged once per suffix (done inside k_rerank)
   }
   CK(ctx, cudaEventRecord(ctx->ev_end, st));
   CK(ctx, cudaMemcpyAsync(ctx->h_LF(), ctx->d_LF, nLF * 4, cudaMemcpyDeviceToHost, st));
@@ -587,7 +592,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_idx[1], N * 4);
   ALLOC(c->d_zero, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)MAX_RERANK_WINDOWS * c->max_aux_tiles * 8 + 64);
   ALLOC(c->d_status, (size_t)MAX_PASSES * c->max_rs_tiles * 1024u);
-  ALLOC(c->d_LF, 256 * 4);
+  ALLOC(c->d_LF, (256 + 8) * 4);
 #undef ALLOC
   if (!rc) {
     e = cudaMallocHost((void**)&c->h_small, (size_t)(CTR_WORDS + HIST_WORDS + 256) * 4);

@@ -888,11 +888,23 @@ struct RerankParams {
   uint32_t ctr_slot;        // ctrl word used as the dynamic tile counter of this launch
 };
 
+// BWT emission fused into the re-rank: the moment a suffix becomes a singleton its rank is final, the records
+// are at hand in SORTED order, so L[rank] = T[id-1] is written with (nearly) consecutive addresses and only the
+// text gather (L2-resident) is random.  No separate N-element byte scatter remains.  The one byte that the block
+// contract moves into the hole (L[N-1] -> out[pidx]) is parked in *lastch for k_finish.
+struct EmitParams {
+  const uint8_t* text;
+  uint8_t* out;
+  uint32_t* lastch;  // bit 8 set = valid
+  uint32_t N;
+  int block_mode;
+};
+
 template <typename KeyT, bool ROUND0>
 __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx,
                                                 uint32_t* __restrict__ rank, RerankParams rp,
                                                 unsigned long long* __restrict__ tstate,
-                                                uint32_t* __restrict__ ctrl) {
+                                                uint32_t* __restrict__ ctrl, EmitParams ep) {
   constexpr int BLOCK = 256, IPT = 8, TILE = BLOCK * IPT, WARPS = BLOCK / 32;
   __shared__ KeyT s_lastkey[BLOCK];
   __shared__ uint32_t s_lastshort[BLOCK];
@@ -1102,6 +1114,11 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
       id[k] %= m;  // timing-only builds carry garbage ids
 #endif
       const bool in_win = (id[k] >= rp.win_lo) && (id[k] < rp.win_hi);
+      if (single && in_win && id[k] > 0) {  // emit L[nr] = T[id-1]  (suffix 0 owns the hole at pidx)
+        const uint8_t ch = ep.text[id[k] - 1];
+        if (ep.block_mode && nr == ep.N - 1) *ep.lastch = 0x100u | ch;
+        else ep.out[nr] = ch;
+      }
       if (single) nr |= RANK_DONE; else if (in_win) ++live;
       if (in_win && (changed || single)) rank[id[k]] = nr;
     }
@@ -1115,59 +1132,29 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
 }
 
 // =====================================================================================================
-// k_final — fused BWT emission + primary index + LFpowers + hole fill.  rank[] is now the inverse suffix
-// array, so in text order (coalesced reads of rank and text):  L[rank[i]] = T[i-1].
+// k_finish — primary index + LFpowers + hole fill (the BWT bytes themselves are emitted by k_rerank as soon
+// as a suffix becomes unique; see EmitParams).  rank[] is now the inverse suffix array.
 //   block contract (BWTransform.cpp:52-64): out[0..n) = L[0..n) with out[pidx] = L[N-1] (hole fill);
 //   raw contract   (divsufsort.c:506-512) : U[r] = L[r] for r != pidx, U[pidx] = T[pidx] ("untouched").
 //   LFpowers[0] = pidx = rank[0]; LFpowers[j] = rank[N - j*(N/nLF)]     (divsufsort.c:337-338,350,381,390,500).
-// The byte scatter lands in an L2-resident output block (<= 126 MB L2 for blocks up to ~100 MiB).
 // Replaces construct_BWT / construct_BWT_orig (divsufsort.c:259-404) and the copy loop (:506-512).
 // =====================================================================================================
-__global__ void __launch_bounds__(256) k_final(const uint32_t* __restrict__ rank, const uint8_t* __restrict__ text,
-                                               uint32_t N, uint8_t* __restrict__ out, int block_mode,
-                                               uint32_t* __restrict__ LF, uint32_t nLF, uint32_t ntiles) {
-  constexpr int IPT = 16;
+__global__ void __launch_bounds__(256) k_finish(const uint32_t* __restrict__ rank, const uint8_t* __restrict__ text,
+                                                uint32_t N, uint8_t* __restrict__ out, int block_mode,
+                                                uint32_t* __restrict__ LF, uint32_t nLF,
+                                                const uint32_t* __restrict__ lastch) {
   const uint32_t pidx = rank[0] & RANK_MASK;
-  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid < nLF) {
+  const uint32_t tid = threadIdx.x;
+  if (tid < nLF) {
     const uint32_t x = N / nLF;
-    LF[gid] = (gid == 0) ? pidx : (rank[N - gid * x] & RANK_MASK);
+    LF[tid] = (tid == 0) ? pidx : (rank[N - tid * x] & RANK_MASK);
   }
-  // 16 consecutive suffixes per thread: four 128-bit rank loads + 16 text bytes in flight per thread
-  for (uint32_t t = gid; t < ntiles * 256u; t += gridDim.x * blockDim.x) {
-    const uint32_t i0 = t * IPT;
-    if (i0 >= N) continue;
-    uint32_t r[IPT];
-    uint8_t ch[IPT];
-    if (i0 + IPT <= N) {
-      const uint4* pr = reinterpret_cast<const uint4*>(rank + i0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 v = pr[q];
-        r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-      }
-#pragma unroll
-      for (int k = 0; k < IPT; ++k) ch[k] = (i0 + k > 0) ? text[i0 + k - 1] : (uint8_t)0;
+  if (tid == 0) {
+    if (block_mode) {
+      const uint32_t lc = *lastch;
+      if (lc & 0x100u) out[pidx] = (uint8_t)(lc & 0xFFu);  // hole fill: begin[LF[0]] = *end (BWTransform.cpp:60)
     } else {
-#pragma unroll
-      for (int k = 0; k < IPT; ++k) {
-        const uint32_t i = i0 + k;
-        r[k] = (i < N) ? rank[i] : 0u;
-        ch[k] = (i < N && i > 0) ? text[i - 1] : (uint8_t)0;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-      const uint32_t i = i0 + k;
-      if (i >= N) break;
-      const uint32_t rr = r[k] & RANK_MASK;
-      if (i == 0) {
-        if (!block_mode) out[pidx] = text[pidx];
-      } else if (block_mode && rr == N - 1) {
-        out[pidx] = ch[k];  // hole fill: begin[LF[0]] = *end
-      } else {
-        out[rr] = ch[k];
-      }
+      out[pidx] = text[pidx];                               // "U[pidx] untouched" (divsufsort.c:506-512)
     }
   }
 }
