@@ -19,9 +19,6 @@ using namespace bwtc_b200;
 
 namespace {
 
-#ifndef BWTC_RS_PERSIST
-#define BWTC_RS_PERSIST 1
-#endif
 constexpr int RS_BLOCK = BWTC_RS_BLOCK;
 constexpr int RS_IPT64 = BWTC_RS_IPT64;
 constexpr int RS_IPT32 = BWTC_RS_IPT32;
@@ -71,8 +68,6 @@ struct bwtc_cuda_ctx {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   int timing_detail = 0;
-  int persist_ctas64 = 148, persist_ctas32 = 148;  // resident CTAs of k_radix_pass_persist
-  int use_persist = BWTC_RS_PERSIST;
   uint32_t force_chars = 0, force_keybytes = 0;
   uint64_t rerank_window_bytes = 72ull << 20;  // rank-scatter window kept L2-resident (126 MB L2)
   uint32_t debug_max_rounds = 0;  // != 0: stop refining after this many rounds (results are then wrong on purpose)
@@ -103,14 +98,6 @@ template <typename KeyT, int IPT, bool IOTA>
 int set_pass_attr(bwtc_cuda_ctx* ctx) {
   CK(ctx, cudaFuncSetAttribute(k_radix_pass<KeyT, RS_BLOCK, IPT, IOTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)RadixPassSmem<KeyT, RS_BLOCK, IPT>::bytes));
-  CK(ctx, cudaFuncSetAttribute(k_radix_pass_persist<KeyT, RS_BLOCK, IPT, IOTA>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)RadixPersistSmem<KeyT, RS_BLOCK, IPT>::bytes));
-  int nb = 0;
-  CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_radix_pass_persist<KeyT, RS_BLOCK, IPT, IOTA>, RS_BLOCK,
-                                                        RadixPersistSmem<KeyT, RS_BLOCK, IPT>::bytes));
-  if (nb < 1) nb = 1;
-  if (sizeof(KeyT) == 8) ctx->persist_ctas64 = nb * ctx->sm_count; else ctx->persist_ctas32 = nb * ctx->sm_count;
   return 0;
 }
 
@@ -154,13 +141,13 @@ void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* pr
     if (chars > cmax) chars = cmax;
     if (chars < 1) chars = 1;
   } else {
-    // An i.i.d. source of entropy H0 separates all but ~2^-6 of N suffixes after need/H0 characters.  If that
+    // An i.i.d. source of entropy H0 separates all but ~2^-5 of N suffixes after need/H0 characters.  If that
     // fits a 32-bit key the round-0 sort moves 8-byte records in <= 4 passes (random bytes, DNA).  Otherwise
     // the source has memory or a small alphabet relative to N (text, repeats): every extra character ordered
     // in round 0 is far cheaper than a doubling round over the suffixes it would leave live (measured:
     // profiles/r01_sweep_round0.md), so the 64-bit key is filled completely.
-    const double need = std::log2((double)N + 1.0) + 6.0;
-    double cn = std::ceil(need / (H0 > 1e-3 ? H0 : 1e-3));
+    const double need = std::log2((double)N + 1.0) + 5.0;
+    double cn = std::ceil(need / (H0 > 1e-3 ? H0 : 1e-3) - 1e-3);
     if (cn > 64) cn = 64;
     const uint32_t c_need = (uint32_t)cn < 1 ? 1 : (uint32_t)cn;
     if (c_need <= cmax32) {
@@ -226,19 +213,7 @@ int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota
     KeyT* kout = static_cast<KeyT*>(ctx->d_keys[cur ^ 1]);
     uint32_t* status = ctx->d_status + (size_t)p * ctx->max_rs_tiles * 256u;
     if (pt->begin()) return BWTC_CUDA_ECUDA;
-    if (ctx->use_persist) {
-      const size_t psmem = RadixPersistSmem<KeyT, RS_BLOCK, IPT>::bytes;
-      const uint32_t resident = (uint32_t)(sizeof(KeyT) == 8 ? ctx->persist_ctas64 : ctx->persist_ctas32);
-      const uint32_t grid = tiles < resident ? tiles : resident;
-      if (iota)
-        k_radix_pass_persist<KeyT, RS_BLOCK, IPT, true><<<grid, RS_BLOCK, psmem, ctx->stream>>>(
-            kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-            CTR_PASS0 + p, iota_top, tiles);
-      else
-        k_radix_pass_persist<KeyT, RS_BLOCK, IPT, false><<<grid, RS_BLOCK, psmem, ctx->stream>>>(
-            kin, ctx->d_idx[cur], kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-            CTR_PASS0 + p, iota_top, tiles);
-    } else if (iota)
+    if (iota)
       k_radix_pass<KeyT, RS_BLOCK, IPT, true><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
           CTR_PASS0 + p, iota_top);
@@ -375,16 +350,9 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     S.kernel_launches++;
     S.algorithmic_bytes += (uint64_t)N + (uint64_t)N * pl.keybytes;
   }
-  CK(ctx, cudaMemcpyAsync(ctx->h_hist(), ctx->d_hist(), pl.npass * 256 * 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));
-  uint32_t mask0 = 0;
-  for (uint32_t p = 0; p < pl.npass; ++p) {
-    bool constant = false;
-    for (int d = 0; d < 256; ++d)
-      if (ctx->h_hist()[p * 256 + d] == N) { constant = true; break; }
-    if (!constant) mask0 |= 1u << p;
-  }
-  if (!mask0) mask0 = 1u;  // the sort must run at least once: it is what materialises the suffix ids
+  // every digit pass of the round runs: a constant digit makes its pass a (stable) identity permutation, and
+  // finding that out would cost a host synchronisation per block
+  const uint32_t mask0 = all0;
   int cur = 0;
   uint32_t pdone = 0;
   int rc;
@@ -405,10 +373,9 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     rp.lo_bits = 0;
     const uint32_t tiles = div_up(N, AUX_TILE);
     const uint32_t nwin = rerank_windows(ctx, N, N);
-    const uint32_t extra_noop = getenv("BWTC_EXP_RERANK_NOOP") ? (uint32_t)atoi(getenv("BWTC_EXP_RERANK_NOOP")) : 0u;
-    for (uint32_t w = 0; w < nwin + extra_noop; ++w) {
-      rp.win_lo = w < nwin ? (uint32_t)((uint64_t)N * w / nwin) : 0u;
-      rp.win_hi = w < nwin ? (uint32_t)((uint64_t)N * (w + 1) / nwin) : 0u;  // w >= nwin: timing experiment, writes nothing
+    for (uint32_t w = 0; w < nwin; ++w) {
+      rp.win_lo = (uint32_t)((uint64_t)N * w / nwin);
+      rp.win_hi = (uint32_t)((uint64_t)N * (w + 1) / nwin);
       rp.ctr_slot = CTR_RERANK + w;
       unsigned long long* ts = ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles;
       if (pl.keybytes == 4)

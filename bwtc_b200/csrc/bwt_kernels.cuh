@@ -36,15 +36,6 @@ constexpr int CTR_WORDS = 32;
 // look-back status words of the radix pass: 2 flag bits + 30-bit count
 constexpr uint32_t LB_AGG = 0x40000000u, LB_PREFIX = 0x80000000u, LB_VALUE = 0x3FFFFFFFu;
 constexpr uint32_t LB_SPIN_LIMIT = 1u << 24;
-#ifndef BWTC_EARLY_PUBLISH
-#define BWTC_EARLY_PUBLISH 0
-#endif
-#ifndef BWTC_EXP_ABLATE
-#define BWTC_EXP_ABLATE 0
-#endif
-#ifndef BWTC_LB_LOAD
-#define BWTC_LB_LOAD 0
-#endif
 #ifndef BWTC_LB_BATCH
 #define BWTC_LB_BATCH 8
 #endif
@@ -81,13 +72,7 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 }
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
-#if BWTC_LB_LOAD == 1
-  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-#elif BWTC_LB_LOAD == 2
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-#else
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-#endif
   return v;
 }
 __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
@@ -112,9 +97,6 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
 
 // Lanes of the warp whose 8-bit digit equals mine (8 ballots; the multi-split primitive of the sort).
 __device__ __forceinline__ uint32_t match_digit8(uint32_t d) {
-#ifdef BWTC_USE_MATCH_ANY
-  return __match_any_sync(0xFFFFFFFFu, d);
-#endif
   uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
@@ -358,7 +340,7 @@ template <typename KeyT, int BLOCK, int IPT>
 struct RadixPassSmem {
   static constexpr int TILE = BLOCK * IPT;
   static constexpr int WARPS = BLOCK / 32;
-  static constexpr size_t bytes = sizeof(KeyT) * TILE + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 256 + 32);
+  static constexpr size_t bytes = sizeof(KeyT) * TILE + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 32);
 };
 
 template <typename KeyT, int BLOCK, int IPT, bool IOTA>
@@ -378,20 +360,14 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
   uint32_t* s_whist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(KeyT) * TILE);
   uint32_t* s_binbase = s_whist + WARPS * 256;
   uint32_t* s_texcl = s_binbase + 256;
-  uint32_t* s_tcnt = s_texcl + 256;
-  uint32_t* s_misc = s_tcnt + 256;  // [0] tile id, [8..15] scan scratch
+  uint32_t* s_misc = s_texcl + 256;  // [0] tile id, [8..15] scan scratch
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef BWTC_PROFILE_STAGES
   const unsigned long long t_entry = clock64();
 #endif
-#ifdef BWTC_EXP_NOTICKET
-  if (tid == 0) s_misc[0] = blockIdx.x;
-#else
   if (tid == 0) s_misc[0] = atomicAdd(&ctrl[ctr_slot], 1u);
-#endif
   for (int i = tid; i < WARPS * 256; i += BLOCK) s_whist[i] = 0;
-  if (tid < 256) s_tcnt[tid] = 0;
   __syncthreads();
   const uint32_t tile = s_misc[0];
 #ifdef BWTC_PROFILE_STAGES
@@ -430,36 +406,8 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
     BWTC_PROF(2);
   }
 #endif
-#if BWTC_EARLY_PUBLISH
-  // ---- count: digit histogram of the tile (shared atomics; one atomic per warp when its 32 digits agree,
-  // which is the common case for the high digits of low-entropy text).  Publishing the counts BEFORE the
-  // expensive ranking decouples the tile chain: by the time this tile looks back, its predecessors have
-  // long since published, so nobody waits on the slowest tile in flight.
-#pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
-    const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, d, 0);
-    if (__all_sync(0xFFFFFFFFu, d == d0)) {
-      if (lane == 0) atomicAdd(&s_tcnt[d0], 32u);
-    } else {
-      atomicAdd(&s_tcnt[d], 1u);
-    }
-  }
-  __syncthreads();
   uint32_t cnt = 0, pub = 0;
   uint32_t* my_status = status + (size_t)tile * 256u + (tid & 255);
-  if (tid < 256) {
-    cnt = s_tcnt[tid];
-    pub = cnt;
-    if (tid == 255) pub -= ((uint32_t)TILE - valid);  // pads are not records
-    st_relaxed_u32(my_status, (tile == 0 ? LB_PREFIX : LB_AGG) | pub);
-  }
-  BWTC_PROF(3);
-
-#else
-  uint32_t cnt = 0, pub = 0;
-  uint32_t* my_status = status + (size_t)tile * 256u + (tid & 255);
-#endif
   // ---- rank inside the warp
   uint16_t lpos[IPT];
   uint32_t* my_hist = s_whist + warp * 256;
@@ -467,21 +415,10 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
     const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
-#if BWTC_EXP_ABLATE == 2 || BWTC_EXP_ABLATE == 4
-    lpos[k] = (uint16_t)(lane + 32 * k);
-    continue;
-#endif
-#if BWTC_EXP_ABLATE == 1
-    const uint32_t m = 1u << lane;
-#else
     const uint32_t m = match_digit8(d);
-#endif
     const int leader = __ffs(m) - 1;
     uint32_t old = 0;
-    if (lane == leader) {
-      old = my_hist[d];
-      my_hist[d] = old + __popc(m);
-    }
+    if (lane == leader) old = atomicAdd(&my_hist[d], (uint32_t)__popc(m));  // one shared-memory RMW, not LDS+STS
     old = __shfl_sync(0xFFFFFFFFu, old, leader);
     lpos[k] = (uint16_t)(old + __popc(m & lt));
     __syncwarp();
@@ -498,24 +435,26 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
       s_whist[w * 256 + tid] = run;
       run += t;
     }
-#if !BWTC_EARLY_PUBLISH
     cnt = run;
     pub = cnt;
     if (tid == 255) pub -= ((uint32_t)TILE - valid);  // pads are not records
     st_relaxed_u32(my_status, (tile == 0 ? LB_PREFIX : LB_AGG) | pub);
-#endif
   }
   const uint32_t texcl = scan256_excl(cnt, s_misc + 8);
   const uint32_t gcount = (tid < 256) ? ghist[tid] : 0u;
   const uint32_t gexcl = scan256_excl(gcount, s_misc + 8);
-  if (tid < 256) s_texcl[tid] = texcl;
+  if (tid < 256) {
+    // fold the tile-local digit offset into every warp's offset: staging then needs ONE digit-indexed lookup
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s_whist[w * 256 + tid] += texcl;
+  }
   __syncthreads();
 
   // ---- ... stage keys in sorted order (needs tile-local offsets only) while predecessors publish
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
     const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
-    const uint32_t p = s_texcl[d] + my_hist[d] + lpos[k];
+    const uint32_t p = my_hist[d] + lpos[k];
     lpos[k] = (uint16_t)p;
     s_keys[p] = key[k];
   }
@@ -524,11 +463,7 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
   // ---- decoupled look-back, one digit per thread, LB_BATCH predecessor words in flight per round trip
   if (tid < 256) {
     uint32_t excl = 0;
-#ifdef BWTC_EXP_NOLOOKBACK
-    if (false) {
-#else
     if (tile != 0) {
-#endif
       long long t = (long long)tile - 1;
       uint32_t spins = 0;
       bool done = false;
@@ -592,11 +527,6 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
     const KeyT kk = s_keys[p];
     const uint32_t d = (uint32_t)(kk >> shift) & 0xFFu;
     gpos[k] = s_binbase[d] + p;
-#if BWTC_EXP_ABLATE >= 3
-    gpos[k] = tile_base + p;  // timing-only: identity placement (perfectly coalesced) to isolate the scatter cost
-#elif BWTC_EXP_ABLATE
-    if (gpos[k] >= n) gpos[k] = p % n;  // timing-only builds produce garbage positions: keep them in range
-#endif
     if (p < valid) keys_out[gpos[k]] = kk;
   }
   __syncthreads();
@@ -610,258 +540,6 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
     if (p < valid) vals_out[gpos[k]] = s_vals[p];
   }
   BWTC_PROF(8);
-}
-
-// =====================================================================================================
-// k_radix_pass_persist — the same digit pass as k_radix_pass, restructured for memory-level parallelism:
-//   * persistent CTAs (grid = resident CTAs), tiles handed out by the same atomic ticket;
-//   * the NEXT tile's keys and ids are prefetched into shared memory with cp.async.bulk (TMA 1-D bulk copy,
-//     completion on an mbarrier) while the current tile is ranked, looked back and scattered, so every CTA
-//     keeps a full tile of loads in flight all the time (the non-persistent kernel only has loads in flight
-//     during ~12% of a CTA's life, which caps it near 3 TB/s by Little's law);
-//   * two shared buffers per CTA: the buffer a tile arrived in is reused to stage that tile in sorted order
-//     (keys and ids side by side, so one scatter loop writes both), then becomes the prefetch target of the
-//     tile after next.
-// Ranking, publication, look-back and the output format are identical to k_radix_pass.
-// =====================================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-template <typename KeyT, int BLOCK, int IPT>
-struct RadixPersistSmem {
-  static constexpr int TILE = BLOCK * IPT;
-  static constexpr int WARPS = BLOCK / 32;
-  static constexpr size_t buf_bytes = (sizeof(KeyT) + 4) * (size_t)TILE;
-  static constexpr size_t bytes = 2 * buf_bytes + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 32) + 2 * 8 + 128;
-};
-
-template <typename KeyT, int BLOCK, int IPT, bool IOTA>
-__global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass_persist(
-    const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
-    uint32_t* __restrict__ vals_out, uint32_t n, uint32_t shift, const uint32_t* __restrict__ ghist,
-    uint32_t* __restrict__ status, uint32_t* __restrict__ ctrl, uint32_t ctr_slot, uint32_t iota_top, uint32_t ntiles) {
-  static_assert(BLOCK >= 256 && BLOCK % 32 == 0, "BLOCK must cover the 256 digit bins");
-  constexpr int TILE = BLOCK * IPT, WARPS = BLOCK / 32;
-  static_assert(TILE <= 65536, "local positions are kept as uint16");
-  constexpr size_t BUF = RadixPersistSmem<KeyT, BLOCK, IPT>::buf_bytes;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* sbase = smem_raw;
-  uint32_t* s_whist = reinterpret_cast<uint32_t*>(sbase + 2 * BUF);
-  uint32_t* s_binbase = s_whist + WARPS * 256;
-  uint32_t* s_texcl = s_binbase + 256;
-  uint32_t* s_misc = s_texcl + 256;  // [0] current tile, [1] next tile, [8..15] scan scratch
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_misc + 32);  // 2 mbarriers
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t lt = lanemask_lt();
-  uint32_t* my_hist = s_whist + warp * 256;
-  constexpr uint32_t KBYTES = (uint32_t)(sizeof(KeyT) * TILE), VBYTES = (uint32_t)(4 * TILE);
-
-  // global digit offsets are the same for every tile of this pass
-  const uint32_t gcount = (tid < 256) ? ghist[tid] : 0u;
-  const uint32_t gexcl = scan256_excl(gcount, s_misc + 8);
-
-  if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t t0 = atomicAdd(&ctrl[ctr_slot], 1u);
-    s_misc[0] = t0;
-    if (t0 < ntiles && (t0 + 1) * (uint32_t)TILE <= n) {  // full tile: bulk prefetch into buffer 0
-      mbar_expect_tx(&s_bar[0], KBYTES + (IOTA ? 0u : VBYTES));
-      bulk_g2s(sbase, keys_in + (size_t)t0 * TILE, KBYTES, &s_bar[0]);
-      if (!IOTA) bulk_g2s(sbase + KBYTES, vals_in + (size_t)t0 * TILE, VBYTES, &s_bar[0]);
-    }
-    s_misc[1] = atomicAdd(&ctrl[ctr_slot], 1u);
-  }
-  __syncthreads();
-
-  uint32_t phase_bits = 0u;  // bit b = parity the next wait on buffer b expects
-  for (uint32_t it = 0;; ++it) {
-    const uint32_t b = it & 1u;
-    const uint32_t tile = s_misc[0];
-    const uint32_t tnext = s_misc[1];
-    if (tile >= ntiles) break;
-    unsigned char* bufc = sbase + (size_t)b * BUF;         // current tile: arrival buffer, then sorted staging
-    unsigned char* bufn = sbase + (size_t)(b ^ 1u) * BUF;  // prefetch target
-    const uint32_t tile_base = tile * (uint32_t)TILE;
-    const uint32_t valid = (n - tile_base < (uint32_t)TILE) ? (n - tile_base) : (uint32_t)TILE;
-    const bool full = (valid == (uint32_t)TILE);
-    __syncthreads();  // everyone has read s_misc[0..1]; previous iteration's scatter reads of bufn are done
-    if (tid == 0) {
-      if (tnext < ntiles && (tnext + 1) * (uint32_t)TILE <= n) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes to bufn precede the async write
-        mbar_expect_tx(&s_bar[b ^ 1u], KBYTES + (IOTA ? 0u : VBYTES));
-        bulk_g2s(bufn, keys_in + (size_t)tnext * TILE, KBYTES, &s_bar[b ^ 1u]);
-        if (!IOTA) bulk_g2s(bufn + KBYTES, vals_in + (size_t)tnext * TILE, VBYTES, &s_bar[b ^ 1u]);
-      }
-      s_misc[0] = tnext;                                  // becomes "current" at the next iteration
-      s_misc[1] = atomicAdd(&ctrl[ctr_slot], 1u);         // ticket two tiles ahead, latency hidden
-    }
-    for (int i = tid; i < WARPS * 256; i += BLOCK) s_whist[i] = 0;
-
-    // ---- current tile -> registers (warp-striped)
-    KeyT key[IPT];
-    uint32_t val[IPT];
-    const uint32_t lfirst = warp * (32 * IPT) + lane;
-    if (full) {
-      mbar_wait(&s_bar[b], (phase_bits >> b) & 1u);
-      phase_bits ^= 1u << b;
-      const KeyT* sk = reinterpret_cast<const KeyT*>(bufc);
-      const uint32_t* sv = reinterpret_cast<const uint32_t*>(bufc + KBYTES);
-#pragma unroll
-      for (int k = 0; k < IPT; ++k) key[k] = sk[lfirst + 32 * k];
-#pragma unroll
-      for (int k = 0; k < IPT; ++k) val[k] = IOTA ? (iota_top - (tile_base + lfirst + 32 * k)) : sv[lfirst + 32 * k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < IPT; ++k) {
-        const uint32_t g = tile_base + lfirst + 32 * k;
-        key[k] = (g < n) ? keys_in[g] : (KeyT)~(KeyT)0;  // pads: digit 255, last in index order
-        val[k] = (g < n) ? (IOTA ? (iota_top - g) : vals_in[g]) : 0u;
-      }
-    }
-    __syncthreads();  // bufc fully consumed (it is the staging buffer from here on); s_whist zeroed
-
-    // ---- rank inside the warp
-    uint16_t lpos[IPT];
-#pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-      const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
-      const uint32_t m = match_digit8(d);
-      const int leader = __ffs(m) - 1;
-      uint32_t old = 0;
-      if (lane == leader) {
-        old = my_hist[d];
-        my_hist[d] = old + __popc(m);
-      }
-      old = __shfl_sync(0xFFFFFFFFu, old, leader);
-      lpos[k] = (uint16_t)(old + __popc(m & lt));
-      __syncwarp();
-    }
-    __syncthreads();
-
-    // ---- per-digit scan over warps, publish the tile's digit counts
-    uint32_t cnt = 0, pub = 0;
-    uint32_t* my_status = status + (size_t)tile * 256u + (tid & 255);
-    if (tid < 256) {
-      uint32_t run = 0;
-#pragma unroll
-      for (int w = 0; w < WARPS; ++w) {
-        const uint32_t t = s_whist[w * 256 + tid];
-        s_whist[w * 256 + tid] = run;
-        run += t;
-      }
-      cnt = run;
-      pub = cnt;
-      if (tid == 255) pub -= ((uint32_t)TILE - valid);  // pads are not records
-      st_relaxed_u32(my_status, (tile == 0 ? LB_PREFIX : LB_AGG) | pub);
-    }
-    const uint32_t texcl = scan256_excl(cnt, s_misc + 8);
-    if (tid < 256) s_texcl[tid] = texcl;
-    __syncthreads();
-
-    // ---- stage keys AND ids in sorted order into the arrival buffer
-    {
-      KeyT* sk = reinterpret_cast<KeyT*>(bufc);
-      uint32_t* sv = reinterpret_cast<uint32_t*>(bufc + KBYTES);
-#pragma unroll
-      for (int k = 0; k < IPT; ++k) {
-        const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
-        const uint32_t p = s_texcl[d] + my_hist[d] + lpos[k];
-        sk[p] = key[k];
-        sv[p] = val[k];
-      }
-    }
-
-    // ---- decoupled look-back, one digit per thread
-    if (tid < 256) {
-      uint32_t excl = 0;
-      if (tile != 0) {
-        long long t = (long long)tile - 1;
-        uint32_t spins = 0;
-        bool done = false;
-        while (!done) {
-          uint32_t v[LB_BATCH];
-#pragma unroll
-          for (int i = 0; i < LB_BATCH; ++i) {
-            const long long ti = t - i;
-            v[i] = (ti >= 0) ? ld_relaxed_u32(status + (size_t)ti * 256u + tid) : LB_PREFIX;
-          }
-          int consumed = 0;
-          bool stop = false;
-#pragma unroll
-          for (int i = 0; i < LB_BATCH; ++i) {
-            if (!stop) {
-              if (v[i] & LB_PREFIX) {
-                excl += v[i] & LB_VALUE;
-                done = true;
-                stop = true;
-              } else if (v[i] & LB_AGG) {
-                excl += v[i] & LB_VALUE;
-                ++consumed;
-              } else {
-                stop = true;
-              }
-            }
-          }
-          t -= consumed;
-          if (!done && consumed == 0) {
-            if (++spins > LB_SPIN_LIMIT) {
-              atomicExch(&ctrl[CTR_ERR], 1u);
-              break;
-            }
-            __nanosleep(20);
-          }
-        }
-        st_relaxed_u32(my_status, LB_PREFIX | ((excl + pub) & LB_VALUE));
-      }
-      s_binbase[tid] = gexcl + excl - texcl;  // + local position = global position (mod 2^32)
-    }
-    __syncthreads();
-
-    // ---- coalesced scatter of keys and ids
-    {
-      const KeyT* sk = reinterpret_cast<const KeyT*>(bufc);
-      const uint32_t* sv = reinterpret_cast<const uint32_t*>(bufc + KBYTES);
-#pragma unroll
-      for (int k = 0; k < IPT; ++k) {
-        const uint32_t p = tid + k * BLOCK;
-        const KeyT kk = sk[p];
-        const uint32_t vv = sv[p];
-        const uint32_t d = (uint32_t)(kk >> shift) & 0xFFu;
-        const uint32_t g = s_binbase[d] + p;
-        if (p < valid) {
-          keys_out[g] = kk;
-          vals_out[g] = vv;
-        }
-      }
-    }
-  }
 }
 
 // =====================================================================================================
@@ -1110,9 +788,6 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
         nr = (uint32_t)(key[k] >> rp.lo_bits) + (HF - HH);
         changed = (HF != HH);
       }
-#if BWTC_EXP_ABLATE
-      id[k] %= m;  // timing-only builds carry garbage ids
-#endif
       const bool in_win = (id[k] >= rp.win_lo) && (id[k] < rp.win_hi);
       if (single && in_win && id[k] > 0) {  // emit L[nr] = T[id-1]  (suffix 0 owns the hole at pidx)
         const uint8_t ch = ep.text[id[k] - 1];
