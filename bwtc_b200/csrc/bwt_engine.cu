@@ -327,7 +327,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   ep.lastch = ctx->d_LF + 256;
   ep.N = N;
   ep.block_mode = block_mode ? 1 : 0;
-  CK(ctx, cudaMemsetAsync(ctx->d_LF + 256, 0, 4, st));
+  CK(ctx, cudaMemsetAsync(ctx->d_LF + 256, 0, 8, st));  // [256] parked hole byte, [257] tail-kernel watchdog
   S.sigma = pl.sigma;
   S.bits_per_char = pl.bits;
   S.chars_round0 = pl.chars;
@@ -380,10 +380,10 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       unsigned long long* ts = ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles;
       if (pl.keybytes == 4)
         k_rerank<uint32_t, true><<<tiles, 256, 0, st>>>(static_cast<const uint32_t*>(ctx->d_keys[cur]), ctx->d_idx[cur],
-                                                        ctx->d_rank, rp, ts, ctx->d_ctrl(), ep);
+                                                        ctx->d_rank, rp, ts, ctx->d_ctrl(), ep, ctx->d_idx[cur ^ 1]);
       else
         k_rerank<unsigned long long, true><<<tiles, 256, 0, st>>>(
-            static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp, ts, ctx->d_ctrl(), ep);
+            static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp, ts, ctx->d_ctrl(), ep, ctx->d_idx[cur ^ 1]);
       CK(ctx, cudaGetLastError());
       S.kernel_launches++;
     }
@@ -412,18 +412,43 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     }
     const uint32_t r = S.rounds;
     const uint32_t m = live;
+    const uint32_t h32 = (uint32_t)(h > 0x7FFFFFFFull ? 0x7FFFFFFFull : h);
+    const uint32_t* live_list = ctx->d_idx[cur ^ 1];  // appended by the k_rerank launches of the previous round
+    if (m <= (uint32_t)SMALL_MAX) {
+      // tail: one CTA finishes all remaining rounds on the device
+      k_small_rounds<<<1, 1024, 0, st>>>(live_list, m, ctx->d_rank, N, h32, ep, ctx->d_LF + 257);
+      CK(ctx, cudaGetLastError());
+      S.kernel_launches++;
+      S.algorithmic_bytes += (uint64_t)m * 24;
+      S.live[r] = m;
+      S.passes[r] = 0;
+      S.prefix_len[r] = h32;
+      S.rounds = r + 1;
+      live = 0;
+      break;
+    }
+    const bool from_list = ((uint64_t)m * 8 <= (uint64_t)N);
     if (zero_round_state(ctx, m, RS_TILE64, maskd)) return BWTC_CUDA_ECUDA;
-    {
+    if (from_list) {
+      // few live suffixes: gather-build from the list into the (dead) buffer that held the sorted records
+      const uint32_t bt = div_up(m, 256);
+      const int grid = (int)(bt < (uint32_t)(ctx->sm_count * 8) ? bt : (uint32_t)(ctx->sm_count * 8));
+      k_build_from_list<<<grid, 256, 0, st>>>(live_list, m, ctx->d_rank, N, h32, lo_bits,
+                                              static_cast<unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur],
+                                              ctx->d_hist(), (int)npassd);
+      CK(ctx, cudaGetLastError());
+      S.kernel_launches++;
+      S.algorithmic_bytes += (uint64_t)m * (4 + 8 + 12);
+    } else {
       const uint32_t btiles = div_up(N, AUX_TILE);
       const int grid = (int)(btiles < (uint32_t)(ctx->sm_count * 8) ? btiles : (uint32_t)(ctx->sm_count * 8));
-      k_build_keys<<<grid, 256, 0, st>>>(ctx->d_rank, N, (uint32_t)(h > 0xFFFFFFFFull ? 0xFFFFFFFFull : h), lo_bits,
-                                         static_cast<unsigned long long*>(ctx->d_keys[0]), ctx->d_idx[0], ctx->d_ctrl(),
-                                         ctx->d_hist(), (int)npassd, btiles);
+      k_build_keys<<<grid, 256, 0, st>>>(ctx->d_rank, N, h32, lo_bits, static_cast<unsigned long long*>(ctx->d_keys[0]),
+                                         ctx->d_idx[0], ctx->d_ctrl(), ctx->d_hist(), (int)npassd, btiles);
       CK(ctx, cudaGetLastError());
       S.kernel_launches++;
       S.algorithmic_bytes += (uint64_t)N * 4 + (uint64_t)m * 12;
+      cur = 0;
     }
-    cur = 0;
     rc = run_sort<unsigned long long, RS_IPT64>(ctx, m, maskd, false, 0, &cur, &pt, &pdone);
     if (rc) return rc;
     {
@@ -438,7 +463,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
         rp.ctr_slot = CTR_RERANK + w;
         k_rerank<unsigned long long, false><<<div_up(m, AUX_TILE), 256, 0, st>>>(
             static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp,
-            ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl(), ep);
+            ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl(), ep, ctx->d_idx[cur ^ 1]);
         CK(ctx, cudaGetLastError());
         S.kernel_launches++;
       }
@@ -450,13 +475,13 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       set_err(ctx->err, "look-back watchdog fired in round %u (code %u)", r, ctx->h_ctrl()[CTR_ERR]);
       return BWTC_CUDA_EINTERNAL;
     }
-    if (ctx->h_ctrl()[CTR_CURSOR] != m) {
+    if (!from_list && ctx->h_ctrl()[CTR_CURSOR] != m) {
       set_err(ctx->err, "round %u: k_build_keys emitted %u records, expected %u", r, ctx->h_ctrl()[CTR_CURSOR], m);
       return BWTC_CUDA_EINTERNAL;
     }
     S.live[r] = m;
     S.passes[r] = pdone;
-    S.prefix_len[r] = (uint32_t)(h > 0xFFFFFFFFull ? 0xFFFFFFFFull : h);
+    S.prefix_len[r] = h32;
     S.rounds = r + 1;
     live = ctx->h_ctrl()[CTR_LIVE];
     ctx->last_cur = cur;
@@ -472,8 +497,13 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   }
   CK(ctx, cudaEventRecord(ctx->ev_end, st));
   CK(ctx, cudaMemcpyAsync(ctx->h_LF(), ctx->d_LF, nLF * 4, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_LF + 257, 4, cudaMemcpyDeviceToHost, st));
   if (!out_dev) CK(ctx, cudaMemcpyAsync(h_out, ctx->d_out, n, cudaMemcpyDeviceToHost, st));
   CK(ctx, cudaStreamSynchronize(st));
+  if (ctx->h_ctrl()[0]) {
+    set_err(ctx->err, "tail refinement kernel did not converge (code %u)", ctx->h_ctrl()[0]);
+    return BWTC_CUDA_EINTERNAL;
+  }
   for (uint32_t j = 0; j < nLF; ++j) LF[j] = ctx->h_LF()[j];
   float ms = 0;
   CK(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));

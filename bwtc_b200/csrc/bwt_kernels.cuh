@@ -582,7 +582,8 @@ template <typename KeyT, bool ROUND0>
 __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx,
                                                 uint32_t* __restrict__ rank, RerankParams rp,
                                                 unsigned long long* __restrict__ tstate,
-                                                uint32_t* __restrict__ ctrl, EmitParams ep) {
+                                                uint32_t* __restrict__ ctrl, EmitParams ep,
+                                                uint32_t* __restrict__ live_out) {
   constexpr int BLOCK = 256, IPT = 8, TILE = BLOCK * IPT, WARPS = BLOCK / 32;
   __shared__ KeyT s_lastkey[BLOCK];
   __shared__ uint32_t s_lastshort[BLOCK];
@@ -769,7 +770,7 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
   exh = max(exh, s_ch);
   const uint32_t nexthead_thread = s_firsthead[tid + 1];
 
-  uint32_t live = 0;
+  uint32_t live = 0, livemask = 0;
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
     const uint32_t j = j0 + k;
@@ -794,17 +795,201 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
         if (ep.block_mode && nr == ep.N - 1) *ep.lastch = 0x100u | ch;
         else ep.out[nr] = ch;
       }
-      if (single) nr |= RANK_DONE; else if (in_win) ++live;
+      if (single) nr |= RANK_DONE; else if (in_win) { ++live; livemask |= 1u << k; }
       if (in_win && (changed || single)) rank[id[k]] = nr;
     }
   }
-  // CTA reduce of live -> one global atomic
+  // The ids still in non-singleton groups are appended to live_out (any order): ctrl[CTR_LIVE] is both the
+  // live count the host reads and the append cursor (one global atomic per tile).  Small next rounds are built
+  // from this list instead of a scan over all N ranks.
+  uint32_t inc = live;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) live += __shfl_down_sync(0xFFFFFFFFu, live, o);
-  if (lane == 0 && live) atomicAdd(&s_live, live);
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // s_wf is free again
+  if (lane == 31) s_wf[warp] = inc;
   __syncthreads();
-  if (tid == 0 && s_live) atomicAdd(&ctrl[CTR_LIVE], s_live);
+  uint32_t woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) {
+    const uint32_t t = s_wf[w];
+    if (w < warp) woff += t;
+    total += t;
+  }
+  if (tid == 0) s_live = total ? atomicAdd(&ctrl[CTR_LIVE], total) : 0u;
+  __syncthreads();
+  if (live_out != nullptr && live) {
+    uint32_t pos = s_live + woff + inc - live;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k)
+      if ((livemask >> k) & 1u) live_out[pos++] = id[k];
+  }
 }
+
+// =====================================================================================================
+// k_build_from_list — doubling-round key build for rounds with few live suffixes: the ids come from the list
+// k_rerank appended (no scan over all N ranks); two rank gathers per record.  Same key layout and fused
+// histograms as k_build_keys.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restrict__ list, uint32_t m,
+                                                         const uint32_t* __restrict__ rank, uint32_t N, uint32_t h,
+                                                         int lo_bits, unsigned long long* __restrict__ keys,
+                                                         uint32_t* __restrict__ idx, uint32_t* __restrict__ hist,
+                                                         int npass) {
+  __shared__ uint32_t s_hist[8 * 256];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) s_hist[p * 256 + tid] = 0;
+  __syncthreads();
+  for (uint32_t j = blockIdx.x * blockDim.x + tid; j < m; j += gridDim.x * blockDim.x) {
+    const uint32_t i = list[j];
+    const uint32_t r = rank[i] & RANK_MASK;
+    const uint32_t r2 = (h < N - i) ? ((rank[i + h] & RANK_MASK) + 1u) : 0u;
+    const unsigned long long key = ((unsigned long long)r << lo_bits) | (unsigned long long)r2;
+    keys[j] = key;
+    idx[j] = i;
+    for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + (uint32_t)((key >> (8 * p)) & 0xFF)], 1u);
+  }
+  __syncthreads();
+  for (int p = 0; p < npass; ++p) {
+    const uint32_t v = s_hist[p * 256 + tid];
+    if (v) atomicAdd(&hist[p * 256 + tid], v);
+  }
+}
+
+// =====================================================================================================
+// k_small_rounds — finishes the refinement when at most SMALL_MAX suffixes are still live: ONE CTA runs all
+// remaining doubling rounds (key build, bitonic sort in shared memory, re-rank, BWT emission, compaction)
+// without returning to the host, instead of ~10 launch-latency-bound kernels per round.
+// Replaces the tail of trsort's loop (trsort.c:563-585), where only a few groups are left.
+// =====================================================================================================
+constexpr int SMALL_MAX = 2048;
+
+__global__ void __launch_bounds__(1024) k_small_rounds(const uint32_t* __restrict__ list, uint32_t m0, uint32_t* rank,
+                                                       uint32_t N, uint32_t h0, EmitParams ep,
+                                                       uint32_t* __restrict__ errflag) {
+  __shared__ unsigned long long s_key[SMALL_MAX];
+  __shared__ uint32_t s_id[SMALL_MAX];
+  __shared__ uint32_t s_a[32], s_b[32];
+  __shared__ uint32_t s_m;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = tid; j < SMALL_MAX; j += 1024) s_id[j] = (j < (int)m0) ? list[j] : 0u;
+  uint32_t m = m0;
+  unsigned long long h = h0;
+  uint32_t iters = 0;
+  __syncthreads();
+  while (m > 0) {
+    if (++iters > 64u) {  // cannot happen (h doubles past N); watchdog instead of a hang
+      if (tid == 0) atomicExch(errflag, 3u);
+      break;
+    }
+    uint32_t P = 2;  // sort width: next power of two >= m
+    while (P < m) P <<= 1;
+    for (uint32_t j = tid; j < P; j += 1024) {
+      unsigned long long key = ~0ull;  // pads sort last
+      if (j < m) {
+        const uint32_t i = s_id[j];
+        const uint32_t hi = rank[i] & RANK_MASK;
+        const uint32_t lo = (h < (unsigned long long)(N - i)) ? ((rank[i + (uint32_t)h] & RANK_MASK) + 1u) : 0u;
+        key = ((unsigned long long)hi << 32) | lo;
+      }
+      s_key[j] = key;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+      for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
+        for (uint32_t t = tid; t < P; t += 1024) {
+          const uint32_t x = t ^ jj;
+          if (x > t) {
+            const unsigned long long a = s_key[t], b = s_key[x];
+            const bool up = ((t & k) == 0);
+            if ((a > b) == up) {
+              s_key[t] = b; s_key[x] = a;
+              const uint32_t ia = s_id[t]; s_id[t] = s_id[x]; s_id[x] = ia;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // re-rank: thread t owns sorted positions 2t and 2t+1
+    unsigned long long key2[2];
+    uint32_t id2[2], hf2[2], hh2[2];
+    uint32_t runf = 0, runh = 0, lf2[2], lh2[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t j = 2 * tid + q;
+      key2[q] = (j < P) ? s_key[j] : ~0ull;
+      id2[q] = (j < P) ? s_id[j] : 0u;
+      const unsigned long long pk = (j > 0 && j <= P) ? s_key[j - 1] : 0ull;
+      hf2[q] = (j == 0 || j >= m || key2[q] != pk) ? 1u : 0u;
+      hh2[q] = (j == 0 || j >= m || (key2[q] >> 32) != (pk >> 32)) ? 1u : 0u;
+      if (hf2[q]) runf = j + 1;
+      if (hh2[q]) runh = j + 1;
+      lf2[q] = runf;
+      lh2[q] = runh;
+    }
+    const unsigned long long nextkey = (2 * tid + 2 < P) ? s_key[2 * tid + 2] : ~0ull;
+    // CTA-wide exclusive max-scan of (runf, runh)
+    uint32_t incf = runf, inch = runh;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t tf = __shfl_up_sync(0xFFFFFFFFu, incf, o), th = __shfl_up_sync(0xFFFFFFFFu, inch, o);
+      if (lane >= o) { incf = max(incf, tf); inch = max(inch, th); }
+    }
+    uint32_t exf = __shfl_up_sync(0xFFFFFFFFu, incf, 1), exh = __shfl_up_sync(0xFFFFFFFFu, inch, 1);
+    if (lane == 0) { exf = 0; exh = 0; }
+    if (lane == 31) { s_a[warp] = incf; s_b[warp] = inch; }
+    __syncthreads();
+    for (int w = 0; w < warp; ++w) { exf = max(exf, s_a[w]); exh = max(exh, s_b[w]); }
+    __syncthreads();
+    uint32_t keep = 0;  // bit q: record stays live
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t j = 2 * tid + q;
+      if (j < m) {
+        const uint32_t HF = max(lf2[q], exf) - 1u, HH = max(lh2[q], exh) - 1u;
+        const unsigned long long nk = (q == 0) ? key2[1] : nextkey;
+        const bool single = hf2[q] && (j + 1 >= m || nk != key2[q]);
+        uint32_t nr = (uint32_t)(key2[q] >> 32) + (HF - HH);
+        if (single && id2[q] > 0) {
+          const uint8_t ch = ep.text[id2[q] - 1];
+          if (ep.block_mode && nr == ep.N - 1) *ep.lastch = 0x100u | ch;
+          else ep.out[nr] = ch;
+        }
+        if (single) nr |= RANK_DONE; else keep |= 1u << q;
+        if (single || HF != HH) rank[id2[q]] = nr;
+      }
+    }
+    // compact the ids that stay live to the front of s_id
+    const uint32_t cnt = __popc(keep);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_a[warp] = inc;
+    __syncthreads();  // also: every thread holds its ids in registers, s_id may be overwritten
+    uint32_t woff = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      const uint32_t t = s_a[w];
+      if (w < warp) woff += t;
+      total += t;
+    }
+    uint32_t pos = woff + inc - cnt;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if ((keep >> q) & 1u) s_id[pos++] = id2[q];
+    if (tid == 0) s_m = total;
+    __syncthreads();  // new list + rank[] updates visible to the whole CTA
+    m = s_m;
+    h = (h * 2 > 0x7FFFFFFFull) ? 0x7FFFFFFFull : h * 2;
+  }
+}
+
 
 // =====================================================================================================
 // k_finish — primary index + LFpowers + hole fill (the BWT bytes themselves are emitted by k_rerank as soon
