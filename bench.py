@@ -341,7 +341,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--depth", type=int, default=3, help="in-flight blocks (contexts) per GPU")
+    ap.add_argument("--depth", type=int, default=6, help="in-flight blocks (contexts) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
