@@ -340,7 +340,7 @@ template <typename KeyT, int BLOCK, int IPT>
 struct RadixPassSmem {
   static constexpr int TILE = BLOCK * IPT;
   static constexpr int WARPS = BLOCK / 32;
-  static constexpr size_t bytes = sizeof(KeyT) * TILE + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 32);
+  static constexpr size_t bytes = (sizeof(KeyT) + 4) * TILE + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 32);
 };
 
 template <typename KeyT, int BLOCK, int IPT, bool IOTA>
@@ -356,8 +356,8 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
   static_assert(TILE <= 65536, "local positions are kept as uint16");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
-  uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw);
-  uint32_t* s_whist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(KeyT) * TILE);
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw + sizeof(KeyT) * TILE);  // ids staged beside the keys
+  uint32_t* s_whist = s_vals + TILE;
   uint32_t* s_binbase = s_whist + WARPS * 256;
   uint32_t* s_texcl = s_binbase + 256;
   uint32_t* s_misc = s_texcl + 256;  // [0] tile id, [8..15] scan scratch
@@ -455,8 +455,8 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
   for (int k = 0; k < IPT; ++k) {
     const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
     const uint32_t p = my_hist[d] + lpos[k];
-    lpos[k] = (uint16_t)p;
     s_keys[p] = key[k];
+    s_vals[p] = val[k];
   }
 
   BWTC_PROF(5);
@@ -520,24 +520,18 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
   }
   __syncthreads();
   BWTC_PROF(6);
-  uint32_t gpos[IPT];
+  // one scatter loop writes key and id of a record (both staged in sorted order)
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
     const uint32_t p = tid + k * BLOCK;
     const KeyT kk = s_keys[p];
+    const uint32_t vv = s_vals[p];
     const uint32_t d = (uint32_t)(kk >> shift) & 0xFFu;
-    gpos[k] = s_binbase[d] + p;
-    if (p < valid) keys_out[gpos[k]] = kk;
-  }
-  __syncthreads();
-  BWTC_PROF(7);
-#pragma unroll
-  for (int k = 0; k < IPT; ++k) s_vals[lpos[k]] = val[k];
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    const uint32_t p = tid + k * BLOCK;
-    if (p < valid) vals_out[gpos[k]] = s_vals[p];
+    const uint32_t g = s_binbase[d] + p;
+    if (p < valid) {
+      keys_out[g] = kk;
+      vals_out[g] = vv;
+    }
   }
   BWTC_PROF(8);
 }
