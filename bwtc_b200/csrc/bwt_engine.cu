@@ -62,6 +62,7 @@ struct bwtc_cuda_ctx {
   uint32_t* d_zero = nullptr;  // [ctrl CTR_WORDS][hist HIST_WORDS][tstate 2*max_aux_tiles] zeroed per round
   uint32_t* d_status = nullptr;  // [MAX_PASSES][max_rs_tiles][256]
   uint32_t* d_LF = nullptr;
+  unsigned long long* d_wtab = nullptr;  // window-sample table: WS_SLOTS keys, WS_SLOTS counters, 2 doubles
   size_t max_rs_tiles = 0, max_aux_tiles = 0;
   // pinned host
   uint32_t* h_small = nullptr;  // [ctrl CTR_WORDS][hist HIST_WORDS][LF 256]
@@ -107,7 +108,7 @@ void ctx_free(bwtc_cuda_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_in); cudaFree(c->d_text); cudaFree(c->d_out); cudaFree(c->d_rank);
   cudaFree(c->d_keys[0]); cudaFree(c->d_keys[1]); cudaFree(c->d_idx[0]); cudaFree(c->d_idx[1]);
-  cudaFree(c->d_zero); cudaFree(c->d_status); cudaFree(c->d_LF);
+  cudaFree(c->d_zero); cudaFree(c->d_status); cudaFree(c->d_LF); cudaFree(c->d_wtab);
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -122,7 +123,8 @@ struct Round0Plan {
 };
 
 // Dense alphabet + round-0 key shape.  present[c] != 0 for every byte of the text.
-void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* present, uint32_t N, Round0Plan* pl) {
+void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* present, uint32_t N,
+                 const double* pair_stats, Round0Plan* pl) {
   uint32_t sigma = 0;
   double total = 0, H0 = 0;
   for (int c = 0; c < 256; ++c) {
@@ -141,23 +143,41 @@ void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* pr
     if (chars > cmax) chars = cmax;
     if (chars < 1) chars = 1;
   } else {
-    // An i.i.d. source of entropy H0 separates all but ~2^-5 of N suffixes after need/H0 characters.  If that
-    // fits a 32-bit key the round-0 sort moves 8-byte records in <= 4 passes (random bytes, DNA).  Otherwise
-    // the source has memory or a small alphabet relative to N (text, repeats): every extra character ordered
-    // in round 0 is far cheaper than a doubling round over the suffixes it would leave live (measured:
-    // profiles/r01_sweep_round0.md), so the 64-bit key is filled completely.
-    const double need = std::log2((double)N + 1.0) + 5.0;
-    double cn = std::ceil(need / (H0 > 1e-3 ? H0 : 1e-3) - 1e-3);
-    if (cn > 64) cn = 64;
-    const uint32_t c_need = (uint32_t)cn < 1 ? 1 : (uint32_t)cn;
-    if (c_need <= cmax32) {
-      keybytes = 4;
-      const uint32_t np = div_up((uint64_t)c_need * b, 8);
-      chars = (8 * np) / b;
-      if (chars > cmax32) chars = cmax32;
-    } else {
+    // Does the source have memory?  Compare the MEASURED collision rate of sampled 8-byte windows with the rate
+    // an i.i.d. source with this byte histogram would show, (sum q^2)^8.  Text and repeats exceed it by orders
+    // of magnitude: they keep many suffixes tied whatever the order-0 statistics say, and every extra character
+    // ordered in round 0 is far cheaper than a doubling round over the suffixes it would leave live (measured:
+    // profiles/r01_experiments.md), so their 64-bit key is filled completely.
+    double q2 = 0.0;
+    for (int c = 0; c < 256; ++c)
+      if (present[c] && count[c]) { const double q = (double)count[c] / total; q2 += q * q; }
+    const double samples = pair_stats[1];
+    const double all_pairs = samples * (samples - 1.0) * 0.5;
+    const double expected = all_pairs * std::pow(q2, 8.0);
+    const bool has_memory = (H0 < 1e-3) || samples < 64.0 || (pair_stats[0] > 8.0 * expected + 16.0);
+    if (has_memory) {
       keybytes = 8;
       chars = cmax64;
+    } else {
+      // i.i.d.-like source (random bytes, DNA): a suffix stays tied after c characters with probability
+      // L(c) = 1 - exp(-N 2^(-H0 c)).  One digit pass over a record costs about the same for 8- and 12-byte
+      // records (the pass is latency-, not byte-bound), a doubling round costs ~npd+2 pass-equivalents per
+      // live record: pick the c that minimises  ceil(c b / 8) + L(c) (npd + 2).
+      const double npd = std::ceil((2.0 * std::log2((double)N + 2.0)) / 8.0);
+      double best = 1e300;
+      chars = cmax64;
+      for (uint32_t c = 1; c <= cmax64; ++c) {
+        const double p0 = std::ceil((double)c * b / 8.0) * ((uint64_t)c * b > 32 ? 1.1 : 1.0);
+        const double L = 1.0 - std::exp(-(double)N * std::exp2(-H0 * (double)c));
+        const double cost = p0 + L * (npd + 2.0);
+        if (cost < best - 1e-9) { best = cost; chars = c; }
+      }
+      // use every bit of the last digit pass that is executed anyway
+      const uint32_t np = div_up((uint64_t)chars * b, 8);
+      const uint32_t cfull = (8 * np) / b;
+      const uint32_t cap = ((uint64_t)chars * b <= 32) ? cmax32 : cmax64;
+      chars = cfull < cap ? cfull : cap;
+      keybytes = ((uint64_t)chars * b <= 32) ? 4 : 8;
     }
   }
   pl->sigma = sigma;
@@ -296,6 +316,23 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   }
   CK(ctx, cudaGetLastError());
   S.kernel_launches++;
+  double* d_pairs = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ctx->d_wtab) + (size_t)WS_SLOTS * 12);
+  {  // sampled 8-byte-window collision statistics for the key-shape policy
+    const uint32_t nbytes = block_mode ? n : N;
+    uint32_t* d_cnt = reinterpret_cast<uint32_t*>(ctx->d_wtab + WS_SLOTS);
+    CK(ctx, cudaMemsetAsync(ctx->d_wtab, 0xFF, (size_t)WS_SLOTS * 8, st));
+    CK(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)WS_SLOTS * 4 + 16, st));
+    if (nbytes >= 8) {
+      uint32_t stride = (nbytes - 7) >> 16;  // ~2^16 samples
+      if (stride < 1) stride = 1;
+      const uint32_t nsamp = (nbytes - 8) / stride + 1;
+      k_window_sample<<<ctx->sm_count * 4, 256, 0, st>>>(d_src, nbytes, stride, nsamp, ctx->d_wtab, d_cnt);
+      k_window_pairs<<<1, 1024, 0, st>>>(d_cnt, d_pairs);
+      CK(ctx, cudaGetLastError());
+      S.kernel_launches += 2;
+    }
+    CK(ctx, cudaMemcpyAsync(ctx->h_LF() + 256, d_pairs, 16, cudaMemcpyDeviceToHost, st));
+  }
   CK(ctx, cudaMemcpyAsync(ctx->h_hist(), ctx->d_hist(), 256 * 4, cudaMemcpyDeviceToHost, st));
   CK(ctx, cudaStreamSynchronize(st));
 
@@ -319,8 +356,10 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     count[last] += 1;
   }
 
+  double pair_stats[2];  // [0] colliding pairs among the sampled 8-byte windows, [1] samples
+  memcpy(pair_stats, ctx->h_LF() + 256, 16);
   Round0Plan pl;
-  plan_round0(ctx, count, present, N, &pl);
+  plan_round0(ctx, count, present, N, pair_stats, &pl);
   EmitParams ep;
   ep.text = d_text;
   ep.out = d_dst;
@@ -590,9 +629,10 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_zero, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)MAX_RERANK_WINDOWS * c->max_aux_tiles * 8 + 64);
   ALLOC(c->d_status, (size_t)MAX_PASSES * c->max_rs_tiles * 1024u);
   ALLOC(c->d_LF, (256 + 8) * 4);
+  ALLOC(c->d_wtab, (size_t)WS_SLOTS * 12 + 64);
 #undef ALLOC
   if (!rc) {
-    e = cudaMallocHost((void**)&c->h_small, (size_t)(CTR_WORDS + HIST_WORDS + 256) * 4);
+    e = cudaMallocHost((void**)&c->h_small, (size_t)(CTR_WORDS + HIST_WORDS + 256 + 8) * 4);
     if (e != cudaSuccess) { set_err(g_err, "cudaMallocHost: %s", cudaGetErrorString(e)); rc = BWTC_CUDA_EALLOC; }
   }
   if (!rc && (cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess)) {

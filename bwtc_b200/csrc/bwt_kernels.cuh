@@ -174,6 +174,62 @@ __global__ void __launch_bounds__(256) k_hist_bytes(const uint8_t* __restrict__ 
 }
 
 // =====================================================================================================
+// k_window_sample / k_window_pairs — policy input for the round-0 key shape.  ~2^16 strided
+// 8-byte windows of the block are inserted into an open-addressing table (atomicCAS on the window itself, a
+// counter per slot); the second kernel reduces sum m(m-1)/2 = number of colliding sample pairs.  The host
+// compares that MEASURED 8-gram collision rate with what an i.i.d. source with the block's byte histogram
+// would give: text and repeats exceed it by orders of magnitude, random bytes and DNA match it.  No source
+// model is assumed beyond that comparison.
+// =====================================================================================================
+constexpr uint32_t WS_SLOTS = 1u << 17;
+constexpr unsigned long long WS_EMPTY = ~0ull;
+
+__global__ void __launch_bounds__(256) k_window_sample(const uint8_t* __restrict__ X, uint32_t n, uint32_t stride,
+                                                       uint32_t nsamp, unsigned long long* __restrict__ tab_key,
+                                                       uint32_t* __restrict__ tab_cnt) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nsamp; s += gridDim.x * blockDim.x) {
+    const uint32_t i = s * stride;  // i + 8 <= n guaranteed by the host
+    unsigned long long key = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) key = (key << 8) | (unsigned long long)X[i + k];
+    if (key == WS_EMPTY) key = WS_EMPTY - 1;
+    unsigned long long hsh = key * 0x9E3779B97F4A7C15ull;
+    uint32_t slot = (uint32_t)(hsh >> 40) & (WS_SLOTS - 1);
+    for (int probe = 0; probe < 64; ++probe) {
+      const unsigned long long prev = atomicCAS(&tab_key[slot], WS_EMPTY, key);
+      if (prev == WS_EMPTY || prev == key) {
+        atomicAdd(&tab_cnt[slot], 1u);
+        break;
+      }
+      slot = (slot + 1) & (WS_SLOTS - 1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_window_pairs(const uint32_t* __restrict__ tab_cnt, double* __restrict__ out) {
+  __shared__ double s_a[32], s_b[32];
+  double pairs = 0.0, tot = 0.0;
+  for (uint32_t i = threadIdx.x; i < WS_SLOTS; i += 1024) {
+    const double m = (double)tab_cnt[i];
+    pairs += m * (m - 1.0) * 0.5;
+    tot += m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pairs += __shfl_down_sync(0xFFFFFFFFu, pairs, o);
+    tot += __shfl_down_sync(0xFFFFFFFFu, tot, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = pairs; s_b[threadIdx.x >> 5] = tot; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, bb = 0;
+    for (int w = 0; w < 32; ++w) { a += s_a[w]; bb += s_b[w]; }
+    out[0] = a;   // colliding sample pairs
+    out[1] = bb;  // samples inserted
+  }
+}
+
+// =====================================================================================================
 // k_pack_round0 — round-0 keys.  Position t of the key array holds suffix i = N-1-t (descending suffix
 // ids, see DESIGN.md §3.2: with a stable sort, suffixes whose c-character window runs past the end of
 // the text then precede every other suffix with an equal key, which is their correct order), so no code
