@@ -56,6 +56,9 @@ class Stats(ctypes.Structure):
         ("sort_ms", ctypes.c_float),
         ("sort_bytes", ctypes.c_uint64),
         ("sort_launches", ctypes.c_uint32),
+        ("sort0_launches", ctypes.c_uint32),
+        ("sort0_bytes", ctypes.c_uint64),
+        ("sort0_ms", ctypes.c_float),
         ("reserved", ctypes.c_uint32),
     ]
 
@@ -68,7 +71,8 @@ class Stats(ctypes.Structure):
             "prefix_len": [int(self.prefix_len[i]) for i in range(r)],
             "kernel_launches": int(self.kernel_launches), "algorithmic_bytes": int(self.algorithmic_bytes),
             "gpu_ms": float(self.gpu_ms), "sort_ms": float(self.sort_ms), "sort_bytes": int(self.sort_bytes),
-            "sort_launches": int(self.sort_launches),
+            "sort_launches": int(self.sort_launches), "sort0_launches": int(self.sort0_launches),
+            "sort0_bytes": int(self.sort0_bytes), "sort0_ms": float(self.sort0_ms),
         }
 
 
@@ -80,6 +84,7 @@ _vp = ctypes.c_void_p
 C_ABI = [
     ("bwtc_cuda_device_count", ctypes.c_int, []),
     ("bwtc_cuda_version", ctypes.c_char_p, []),
+    ("bwtc_cuda_stats_sizeof", ctypes.c_uint32, []),
     ("bwtc_cuda_global_error", ctypes.c_char_p, []),
     ("bwtc_cuda_ctx_create", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_uint32]),
     ("bwtc_cuda_ctx_destroy", None, [_vp]),

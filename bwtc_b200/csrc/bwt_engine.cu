@@ -398,6 +398,9 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   if (pl.keybytes == 4) rc = run_sort<uint32_t, RS_IPT32>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone);
   else rc = run_sort<unsigned long long, RS_IPT64>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone);
   if (rc) return rc;
+  const size_t round0_events = pt.used;
+  S.sort0_launches = S.sort_launches;
+  S.sort0_bytes = S.sort_bytes;
   S.live[0] = N;
   S.passes[0] = pdone;
   S.prefix_len[0] = 0;
@@ -548,13 +551,15 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   CK(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
   S.gpu_ms = ms;
   if (ctx->timing_detail) {
-    float tot = 0;
+    float tot = 0, tot0 = 0;
     for (size_t i = 0; i + 1 < pt.used; i += 2) {
       float t = 0;
       CK(ctx, cudaEventElapsedTime(&t, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
       tot += t;
+      if (i < round0_events) tot0 += t;
     }
     S.sort_ms = tot;
+    S.sort0_ms = tot0;
   }
   return (int64_t)LF[0];
 }
@@ -584,6 +589,8 @@ const char* bwtc_cuda_version(void) {
 }
 
 const char* bwtc_cuda_global_error(void) { return g_err; }
+
+uint32_t bwtc_cuda_stats_sizeof(void) { return (uint32_t)sizeof(bwtc_cuda_stats); }
 
 int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_bytes) {
   if (!out || max_block_bytes == 0) { set_err(g_err, "bad arguments"); return BWTC_CUDA_EARG; }

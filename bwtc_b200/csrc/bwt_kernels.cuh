@@ -96,8 +96,8 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
 }
 
 // Lanes of the warp whose 8-bit digit equals mine (8 ballots; the multi-split primitive of the sort).
-// Inline PTX pins the 4-instruction form per bit (bit test -> predicate, ballot, and two predicated ANDs that
-// ptxas folds into one LOP3 each); the C++ "bit ? bal : ~bal" form compiled to 6 per bit.
+// Inline PTX pins 3 instructions per bit (ballot + one of two predicated LOP3s; the 8 bit-test predicates come
+// from a single R2P); the C++ "bit ? bal : ~bal" form compiled to 6 per bit.
 __device__ __forceinline__ uint32_t match_digit8(uint32_t d) {
   uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
@@ -110,8 +110,7 @@ __device__ __forceinline__ uint32_t match_digit8(uint32_t d) {
         "setp.ne.u32 p, t, 0;\n"
         "vote.sync.ballot.b32 t, p, 0xffffffff;\n"
         "@p and.b32 %0, %0, t;\n"
-        "@!p not.b32 t, t;\n"
-        "@!p and.b32 %0, %0, t;\n"
+        "@!p lop3.b32 %0, %0, t, 0, 0x30;\n"  // m & ~t in one LOP3
         "}\n"
         : "+r"(m)
         : "r"(d), "r"(1u << b));

@@ -61,12 +61,16 @@ typedef struct bwtc_cuda_stats {
   float    sort_ms;                         /* device time inside radix digit passes (only with detailed timing on) */
   uint64_t sort_bytes;                      /* algorithmic bytes moved by the radix digit passes */
   uint32_t sort_launches;                   /* radix digit pass launches */
+  uint32_t sort0_launches;                  /* ... of which round-0 passes (all N records each) */
+  uint64_t sort0_bytes;                     /* algorithmic bytes moved by the round-0 passes */
+  float    sort0_ms;                        /* device time inside the round-0 passes (detailed timing on) */
   uint32_t reserved;
 } bwtc_cuda_stats;
 
 /* ---- library / device ------------------------------------------------------------------------ */
 int         bwtc_cuda_device_count(void);           /* number of CUDA devices, or BWTC_CUDA_ECUDA */
 const char* bwtc_cuda_version(void);
+uint32_t    bwtc_cuda_stats_sizeof(void);           /* sizeof(bwtc_cuda_stats) the library was built with */
 /* Thread-local message of the last failing call that had no context to attach it to. */
 const char* bwtc_cuda_global_error(void);
 

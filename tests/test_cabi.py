@@ -33,6 +33,11 @@ def test_version_string():
     assert b"sm_100a" in lib.bwtc_cuda_version()
 
 
+def test_stats_struct_layout_matches_binding():
+    lib = bw.load_library()
+    assert lib.bwtc_cuda_stats_sizeof() == ctypes.sizeof(bw.Stats)
+
+
 def test_num_starting_points_matches_reference_rules(oracle):
     # BWTManager.cpp:60-64 clamp + BWTBlock.cpp:104-108 sizing
     for n in (1, 2, 255, 256, 257, 1000, 1 << 20):
