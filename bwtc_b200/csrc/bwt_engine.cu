@@ -379,12 +379,36 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   {
     const uint32_t ptiles = div_up(N, AUX_TILE);
     const int grid = (int)(ptiles < (uint32_t)(ctx->sm_count * 4) ? ptiles : (uint32_t)(ctx->sm_count * 4));
-    if (pl.keybytes == 4)
+    // One representative digit per phase class is counted by k_pack_round0; the others are derived (k_hist_derive).
+    uint32_t hist_mask = 0;
+    DeriveParams dp;
+    dp.count = 0;
+    const uint32_t keybits = pl.chars * pl.bits;
+    for (uint32_t p = 0; p < pl.npass; ++p) {
+      int rep = -1;
+      const bool full_p = (8 * p + 8 <= keybits);
+      if (full_p && N > 64)
+        for (uint32_t r = 0; r < p; ++r)
+          if (((hist_mask >> r) & 1u) && (8 * r) % pl.bits == (8 * p) % pl.bits && (8 * (p - r)) % pl.bits == 0) { rep = (int)r; break; }
+      if (rep < 0) {
+        hist_mask |= 1u << p;
+      } else {
+        dp.p[dp.count] = (uint8_t)p;
+        dp.r[dp.count] = (uint8_t)rep;
+        dp.t[dp.count] = (uint8_t)(8 * (p - (uint32_t)rep) / pl.bits);
+        dp.count++;
+      }
+    }
+    if (pl.keybytes == 4) {
       k_pack_round0<uint32_t><<<grid, 256, 0, st>>>(d_text, N, static_cast<uint32_t*>(ctx->d_keys[0]), pl.pp,
-                                                     ctx->d_hist(), (int)pl.npass, ptiles);
-    else
+                                                     ctx->d_hist(), hist_mask, ptiles);
+      if (dp.count) k_hist_derive<uint32_t><<<dp.count, 256, 0, st>>>(d_text, N, pl.pp, dp, ctx->d_hist());
+    } else {
       k_pack_round0<unsigned long long><<<grid, 256, 0, st>>>(d_text, N, static_cast<unsigned long long*>(ctx->d_keys[0]),
-                                                               pl.pp, ctx->d_hist(), (int)pl.npass, ptiles);
+                                                               pl.pp, ctx->d_hist(), hist_mask, ptiles);
+      if (dp.count) k_hist_derive<unsigned long long><<<dp.count, 256, 0, st>>>(d_text, N, pl.pp, dp, ctx->d_hist());
+    }
+    if (dp.count) S.kernel_launches++;
     CK(ctx, cudaGetLastError());
     S.kernel_launches++;
     S.algorithmic_bytes += (uint64_t)N + (uint64_t)N * pl.keybytes;

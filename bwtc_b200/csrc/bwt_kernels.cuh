@@ -245,8 +245,9 @@ __global__ void __launch_bounds__(1024) k_window_pairs(const uint32_t* __restric
 // ids, see DESIGN.md §3.2: with a stable sort, suffixes whose c-character window runs past the end of
 // the text then precede every other suffix with an equal key, which is their correct order), so no code
 // point has to be reserved for the sentinel.  key = c dense b-bit codes, most significant = first char.
-// The digit histograms of ALL radix passes of the round are accumulated here (shared-memory atomics,
-// one global flush per CTA; persistent grid), so the sort never re-reads the keys to count.
+// The digit histograms of the radix passes of the round are accumulated here (shared-memory atomics, one
+// global flush per CTA; persistent grid) — one representative digit per phase class, the others are derived
+// by k_hist_derive — so the sort never re-reads the keys to count.
 // Replaces the bucket counting of sort_typeBstar (divsufsort.c:62-74).
 // =====================================================================================================
 struct PackParams {
@@ -258,7 +259,7 @@ struct PackParams {
 template <typename KeyT>
 __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__ text, uint32_t N,
                                                      KeyT* __restrict__ keys, PackParams pp,
-                                                     uint32_t* __restrict__ hist, int npass, uint32_t ntiles) {
+                                                     uint32_t* __restrict__ hist, uint32_t hist_mask, uint32_t ntiles) {
   constexpr int BLOCK = 256, IPT = 8, TILE = BLOCK * IPT;
   __shared__ uint8_t s_lut[256];
   __shared__ uint8_t s_code[TILE + 64];
@@ -286,15 +287,68 @@ __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__
         KeyT key = 0;
         for (uint32_t j = 0; j < c; ++j) key = (KeyT)(key << b) | (KeyT)s_code[q0 + j];
         keys[t] = key;
-        for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + (uint32_t)((key >> (8 * p)) & 0xFF)], 1u);
+#pragma unroll
+        for (int p = 0; p < (int)(sizeof(KeyT)); ++p)
+          if ((hist_mask >> p) & 1u) atomicAdd(&s_hist[p * 256 + (uint32_t)((key >> (8 * p)) & 0xFF)], 1u);
       }
     }
     __syncthreads();
   }
-  for (int p = 0; p < npass; ++p) {
+#pragma unroll
+  for (int p = 0; p < (int)(sizeof(KeyT)); ++p) {
+    if (!((hist_mask >> p) & 1u)) continue;
     const uint32_t v = s_hist[p * 256 + tid];
     if (v) atomicAdd(&hist[p * 256 + tid], v);
   }
+}
+
+// =====================================================================================================
+// k_hist_derive — the digit histograms of a sliding-window key are shifts of each other.  Digit p of key(i)
+// depends only on the characters i+j_lo(p).. and on the phase (8p mod b) at which the 8-bit digit cuts the b-bit
+// codes; two digits p > r of equal phase satisfy  digit_p(key(i)) == digit_r(key(i - t)),  t = 8(p-r)/b.  So
+//   H_p = H_r - sum_{i=N-t}^{N-1} e(digit_r(key(i))) + sum_{i=0}^{t-1} e(digit_p(key(i)))
+// and k_pack_round0 only has to count one representative digit per phase class with shared-memory atomics
+// (its most expensive part): 3 of 8 digits for 6-bit codes, 1 of 4 for bytes and DNA.  Block q of the grid
+// derives digit derive_p[q] from representative derive_r[q].
+// =====================================================================================================
+struct DeriveParams {
+  uint32_t count;
+  uint8_t p[8], r[8], t[8];
+};
+
+template <typename KeyT>
+__device__ __forceinline__ KeyT pack_key_at(const uint8_t* __restrict__ text, uint32_t N, uint32_t i, const uint8_t* lut,
+                                            uint32_t b, uint32_t c) {
+  KeyT key = 0;
+  for (uint32_t j = 0; j < c; ++j) {
+    const uint32_t g = i + j;
+    key = (KeyT)(key << b) | (KeyT)((g < N) ? lut[text[g]] : 0u);
+  }
+  return key;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256) k_hist_derive(const uint8_t* __restrict__ text, uint32_t N, PackParams pp,
+                                                     DeriveParams dp, uint32_t* __restrict__ hist) {
+  __shared__ uint8_t s_lut[256];
+  __shared__ uint32_t s_h[256];
+  const int tid = threadIdx.x;
+  const uint32_t p = dp.p[blockIdx.x], r = dp.r[blockIdx.x], t = dp.t[blockIdx.x];
+  s_lut[tid] = pp.lut[tid];
+  s_h[tid] = hist[r * 256 + tid];
+  __syncthreads();
+  if ((uint32_t)tid < t) {
+    if ((uint32_t)tid < N) {  // head term: suffix i = tid counted for digit p
+      const KeyT kh = pack_key_at<KeyT>(text, N, (uint32_t)tid, s_lut, pp.bits, pp.chars);
+      atomicAdd(&s_h[(uint32_t)((kh >> (8 * p)) & 0xFF)], 1u);
+    }
+    if ((uint32_t)tid < N) {  // tail term: suffix i = N-1-tid was counted for digit r but has no partner
+      const KeyT kt = pack_key_at<KeyT>(text, N, N - 1u - (uint32_t)tid, s_lut, pp.bits, pp.chars);
+      atomicSub(&s_h[(uint32_t)((kt >> (8 * r)) & 0xFF)], 1u);
+    }
+  }
+  __syncthreads();
+  hist[p * 256 + tid] = s_h[tid];
 }
 
 // =====================================================================================================

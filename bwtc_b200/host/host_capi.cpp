@@ -38,6 +38,9 @@ int bwtc_host_manager_transform(unsigned char* buf, unsigned n, unsigned starts,
   }
 }
 
+/* sizeof(bwtc_cuda_stats) this library was compiled against (must equal bwtc_cuda_stats_sizeof()). */
+unsigned bwtc_host_stats_sizeof(void) { return (unsigned)sizeof(bwtc_cuda_stats); }
+
 int bwtc_host_is_valid_choice(char c) { return bwtc_b200::BWTManager::isValidChoice(c) ? 1 : 0; }
 
 }  // extern "C"
