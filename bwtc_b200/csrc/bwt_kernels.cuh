@@ -278,18 +278,45 @@ __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__
       s_code[q] = (g >= 0 && g < (long long)N) ? s_lut[text[g]] : (uint8_t)0;
     }
     __syncthreads();
+    // Thread-blocked: 8 consecutive positions per thread.  Position t holds suffix N-1-t, so walking t upwards
+    // walks the text downwards and each key is the previous one shifted by one character plus one new code:
+    //   key(i) = code(T[i]) << (c-1)b | key(i+1) >> b        (1 shared-memory byte per key instead of c)
+    {
+      const uint32_t u0 = (uint32_t)tid * IPT;
+      const int q0 = TILE - 1 - (int)u0;  // s_code index of the first character of the thread's first suffix
+      KeyT key = 0;
+      for (uint32_t j = 0; j < c; ++j) key = (KeyT)(key << b) | (KeyT)s_code[q0 + j];
+      const uint32_t topshift = (c - 1) * b;
+      KeyT out[IPT];
 #pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-      const uint32_t u = k * BLOCK + tid;
-      const uint32_t t = t0 + u;
-      if (t < N) {
-        const int q0 = TILE - 1 - (int)u;
-        KeyT key = 0;
-        for (uint32_t j = 0; j < c; ++j) key = (KeyT)(key << b) | (KeyT)s_code[q0 + j];
-        keys[t] = key;
+      for (int k = 0; k < IPT; ++k) {
+        if (k > 0) key = (KeyT)((KeyT)s_code[q0 - k] << topshift) | (KeyT)(key >> b);
+        out[k] = key;
+      }
+      const uint32_t t = t0 + u0;
+      if (t + IPT <= N) {
+        if (sizeof(KeyT) == 8) {
+          ulonglong2* dst = reinterpret_cast<ulonglong2*>(keys + t);  // t % 8 == 0, keys 256-byte aligned
 #pragma unroll
-        for (int p = 0; p < (int)(sizeof(KeyT)); ++p)
-          if ((hist_mask >> p) & 1u) atomicAdd(&s_hist[p * 256 + (uint32_t)((key >> (8 * p)) & 0xFF)], 1u);
+          for (int k = 0; k < IPT; k += 2) dst[k / 2] = make_ulonglong2((unsigned long long)out[k], (unsigned long long)out[k + 1]);
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(keys + t);
+#pragma unroll
+          for (int k = 0; k < IPT; k += 4)
+            dst[k / 4] = make_uint4((uint32_t)out[k], (uint32_t)out[k + 1], (uint32_t)out[k + 2], (uint32_t)out[k + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+          if (t + k < N) keys[t + k] = out[k];
+      }
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        if (t + k < N) {
+#pragma unroll
+          for (int p = 0; p < (int)(sizeof(KeyT)); ++p)
+            if ((hist_mask >> p) & 1u) atomicAdd(&s_hist[p * 256 + (uint32_t)((out[k] >> (8 * p)) & 0xFF)], 1u);
+        }
       }
     }
     __syncthreads();
