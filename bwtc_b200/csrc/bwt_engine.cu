@@ -194,6 +194,7 @@ uint32_t rerank_windows(const bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m) {
   if ((uint64_t)m * 4 < (uint64_t)N) return 1;  // few scattered writes: a second read of the records costs more
   uint64_t w = ((uint64_t)N * 4 + ctx->rerank_window_bytes - 1) / ctx->rerank_window_bytes;
   if (w < 1) w = 1;
+  if (w > 8) w = 8;  // measured (256 MiB block): beyond 8 windows the re-reads cost more than the L2 residency saves
   if (w > MAX_RERANK_WINDOWS) w = MAX_RERANK_WINDOWS;
   return (uint32_t)w;
 }
@@ -257,9 +258,9 @@ int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota
   return 0;
 }
 
-int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t rs_tile, uint32_t pass_mask) {
+int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m, uint32_t rs_tile, uint32_t pass_mask) {
   const uint32_t aux_tiles = div_up(m, AUX_TILE);
-  CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)MAX_RERANK_WINDOWS * ctx->max_aux_tiles * 8, ctx->stream));
+  CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)rerank_windows(ctx, N, m) * ctx->max_aux_tiles * 8, ctx->stream));
   const uint32_t tiles = div_up(m, rs_tile);
   for (int p = 0; p < MAX_PASSES; ++p)
     if ((pass_mask >> p) & 1u)
@@ -375,7 +376,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   // ---- round 0: pack keys (+ all digit histograms), sort, re-rank
   const uint32_t rs_tile0 = pl.keybytes == 4 ? RS_TILE32 : RS_TILE64;
   const uint32_t all0 = (1u << pl.npass) - 1u;
-  if (zero_round_state(ctx, N, rs_tile0, all0)) return BWTC_CUDA_ECUDA;
+  if (zero_round_state(ctx, N, N, rs_tile0, all0)) return BWTC_CUDA_ECUDA;
   {
     const uint32_t ptiles = div_up(N, AUX_TILE);
     const int grid = (int)(ptiles < (uint32_t)(ctx->sm_count * 4) ? ptiles : (uint32_t)(ctx->sm_count * 4));
@@ -494,7 +495,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       break;
     }
     const bool from_list = ((uint64_t)m * 8 <= (uint64_t)N);
-    if (zero_round_state(ctx, m, RS_TILE64, maskd)) return BWTC_CUDA_ECUDA;
+    if (zero_round_state(ctx, N, m, RS_TILE64, maskd)) return BWTC_CUDA_ECUDA;
     if (from_list) {
       // few live suffixes: gather-build from the list into the (dead) buffer that held the sorted records
       const uint32_t bt = div_up(m, 256);

@@ -26,12 +26,12 @@ constexpr uint32_t RANK_MASK = 0x7FFFFFFFu;
 
 // ---- control words (one uint32 array per context, zeroed by a memset at the start of every round)
 constexpr int CTR_PASS0 = 0;       // [0..15]  dynamic tile counters of the radix passes of this round
-constexpr int CTR_RERANK = 20;     // [20..27] dynamic tile counters of the k_rerank window launches
-constexpr int MAX_RERANK_WINDOWS = 8;
+constexpr int CTR_RERANK = 32;     // [32..47] dynamic tile counters of the k_rerank window launches
+constexpr int MAX_RERANK_WINDOWS = 16;
 constexpr int CTR_CURSOR = 17;     // output cursor of k_build_keys (== number of live records emitted)
 constexpr int CTR_LIVE = 18;       // records still in non-singleton groups after k_rerank
 constexpr int CTR_ERR = 19;        // != 0: a look-back watchdog fired (engine returns BWTC_CUDA_EINTERNAL)
-constexpr int CTR_WORDS = 32;
+constexpr int CTR_WORDS = 64;
 
 // look-back status words of the radix pass: 2 flag bits + 30-bit count
 constexpr uint32_t LB_AGG = 0x40000000u, LB_PREFIX = 0x80000000u, LB_VALUE = 0x3FFFFFFFu;
