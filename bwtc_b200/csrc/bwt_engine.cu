@@ -62,6 +62,7 @@ struct bwtc_cuda_ctx {
   uint32_t* d_zero = nullptr;  // [ctrl CTR_WORDS][hist HIST_WORDS][tstate 2*max_aux_tiles] zeroed per round
   uint32_t* d_status = nullptr;  // [MAX_PASSES][max_rs_tiles][256]
   uint32_t* d_LF = nullptr;
+  uint32_t* d_tilecnt = nullptr;  // [2][max_aux_tiles]: per-tile live counts of k_rerank and their exclusive prefix
   unsigned long long* d_wtab = nullptr;  // window-sample table: WS_SLOTS keys, WS_SLOTS counters, 2 doubles
   size_t max_rs_tiles = 0, max_aux_tiles = 0;
   // pinned host
@@ -69,6 +70,7 @@ struct bwtc_cuda_ctx {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   int timing_detail = 0;
+  int use_seg = 1;  // segmented (sort-free) doubling rounds when every group is small
   uint32_t force_chars = 0, force_keybytes = 0;
   uint64_t rerank_window_bytes = 72ull << 20;  // rank-scatter window kept L2-resident (126 MB L2)
   uint32_t debug_max_rounds = 0;  // != 0: stop refining after this many rounds (results are then wrong on purpose)
@@ -108,7 +110,7 @@ void ctx_free(bwtc_cuda_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_in); cudaFree(c->d_text); cudaFree(c->d_out); cudaFree(c->d_rank);
   cudaFree(c->d_keys[0]); cudaFree(c->d_keys[1]); cudaFree(c->d_idx[0]); cudaFree(c->d_idx[1]);
-  cudaFree(c->d_zero); cudaFree(c->d_status); cudaFree(c->d_LF); cudaFree(c->d_wtab);
+  cudaFree(c->d_zero); cudaFree(c->d_status); cudaFree(c->d_LF); cudaFree(c->d_wtab); cudaFree(c->d_tilecnt);
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -445,12 +447,14 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       rp.win_hi = (uint32_t)((uint64_t)N * (w + 1) / nwin);
       rp.ctr_slot = CTR_RERANK + w;
       unsigned long long* ts = ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles;
+      StageParams sp{reinterpret_cast<uint32_t*>(ctx->d_keys[cur ^ 1]), reinterpret_cast<uint32_t*>(ctx->d_keys[cur ^ 1]) + N,
+                     ctx->d_tilecnt, w == 0 ? 1 : 0};
       if (pl.keybytes == 4)
         k_rerank<uint32_t, true><<<tiles, 256, 0, st>>>(static_cast<const uint32_t*>(ctx->d_keys[cur]), ctx->d_idx[cur],
-                                                        ctx->d_rank, rp, ts, ctx->d_ctrl(), ep, ctx->d_idx[cur ^ 1]);
+                                                        ctx->d_rank, rp, ts, ctx->d_ctrl(), ep, sp);
       else
         k_rerank<unsigned long long, true><<<tiles, 256, 0, st>>>(
-            static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp, ts, ctx->d_ctrl(), ep, ctx->d_idx[cur ^ 1]);
+            static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp, ts, ctx->d_ctrl(), ep, sp);
       CK(ctx, cudaGetLastError());
       S.kernel_launches++;
     }
@@ -463,7 +467,31 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     return BWTC_CUDA_EINTERNAL;
   }
   uint32_t live = ctx->h_ctrl()[CTR_LIVE];
+  uint32_t maxgroup = ctx->h_ctrl()[CTR_MAXGROUP];
+  uint32_t m_prev = N;  // records of the last global sort = extent of the k_rerank staging slots
+  // six u32[N] work arrays: halves of the two key buffers and the two id buffers
+  uint32_t* pool[6] = {reinterpret_cast<uint32_t*>(ctx->d_keys[0]), reinterpret_cast<uint32_t*>(ctx->d_keys[0]) + N,
+                       reinterpret_cast<uint32_t*>(ctx->d_keys[1]), reinterpret_cast<uint32_t*>(ctx->d_keys[1]) + N,
+                       ctx->d_idx[0], ctx->d_idx[1]};
+  int list_nr = -1, list_id = -1;  // pool indices of the compact, rank-ordered (rank, id) lists of the live suffixes
+  bool have_lists = false, after_seg = false;
   ctx->last_cur = cur;
+
+  // Concatenate the per-tile chunks k_rerank staged (in d_keys[cur^1]) into compact lists in d_keys[cur], whose
+  // sorted keys are dead by now.  Tile order is kept, so every group stays contiguous.
+  auto make_lists = [&]() -> int {
+    const uint32_t tiles = div_up(m_prev, AUX_TILE);
+    k_scan_tile_counts<<<1, 1024, 0, st>>>(ctx->d_tilecnt, ctx->d_tilecnt + ctx->max_aux_tiles, tiles);
+    k_gather_chunks<<<tiles, 256, 0, st>>>(pool[2 * (cur ^ 1)], pool[2 * (cur ^ 1) + 1], ctx->d_tilecnt,
+                                           ctx->d_tilecnt + ctx->max_aux_tiles, AUX_TILE, pool[2 * cur], pool[2 * cur + 1]);
+    CK(ctx, cudaGetLastError());
+    S.kernel_launches += 2;
+    S.algorithmic_bytes += (uint64_t)live * 16;
+    list_nr = 2 * cur;
+    list_id = 2 * cur + 1;
+    have_lists = true;
+    return 0;
+  };
 
   // ---- doubling rounds
   const int lo_bits = (int)ceil_log2_u64((uint64_t)N + 1);
@@ -480,10 +508,11 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     const uint32_t r = S.rounds;
     const uint32_t m = live;
     const uint32_t h32 = (uint32_t)(h > 0x7FFFFFFFull ? 0x7FFFFFFFull : h);
-    const uint32_t* live_list = ctx->d_idx[cur ^ 1];  // appended by the k_rerank launches of the previous round
+
     if (m <= (uint32_t)SMALL_MAX) {
       // tail: one CTA finishes all remaining rounds on the device
-      k_small_rounds<<<1, 1024, 0, st>>>(live_list, m, ctx->d_rank, N, h32, ep, ctx->d_LF + 257);
+      if (!have_lists && make_lists()) return BWTC_CUDA_ECUDA;
+      k_small_rounds<<<1, 1024, 0, st>>>(pool[list_id], m, ctx->d_rank, N, h32, ep, ctx->d_LF + 257);
       CK(ctx, cudaGetLastError());
       S.kernel_launches++;
       S.algorithmic_bytes += (uint64_t)m * 24;
@@ -494,18 +523,60 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       live = 0;
       break;
     }
+
+    if (ctx->use_seg && maxgroup <= (uint32_t)SEG_MAXGROUP) {
+      // every group is small: order each group locally, no global sort (k_seg_round + k_apply_ranks)
+      if (!have_lists && make_lists()) return BWTC_CUDA_ECUDA;
+      int free_idx[4], nf = 0;
+      for (int q = 0; q < 6; ++q)
+        if (q != list_nr && q != list_id) free_idx[nf++] = q;
+      const int out_nr = free_idx[0], out_id = free_idx[1], up_a = free_idx[2], up_b = free_idx[3];
+      CK(ctx, cudaMemsetAsync(ctx->d_ctrl(), 0, CTR_WORDS * 4, st));
+      k_seg_round<<<div_up(m, SEG_T), 256, 0, st>>>(pool[list_nr], pool[list_id], m, ctx->d_rank, N, h32, ep, pool[out_nr],
+                                                    pool[out_id], pool[up_a], pool[up_b], ctx->d_ctrl());
+      k_apply_ranks<<<ctx->sm_count * 4, 256, 0, st>>>(pool[up_a], pool[up_b], ctx->d_ctrl(), ctx->d_rank);
+      CK(ctx, cudaGetLastError());
+      S.kernel_launches += 2;
+      S.algorithmic_bytes += (uint64_t)m * 32;
+      CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_WORDS * 4, cudaMemcpyDeviceToHost, st));
+      CK(ctx, cudaStreamSynchronize(st));
+      if (ctx->h_ctrl()[CTR_ERR]) {
+        set_err(ctx->err, "segmented round %u failed (code %u)", r, ctx->h_ctrl()[CTR_ERR]);
+        return BWTC_CUDA_EINTERNAL;
+      }
+      S.live[r] = m;
+      S.passes[r] = 0;
+      S.prefix_len[r] = h32;
+      S.rounds = r + 1;
+      live = ctx->h_ctrl()[CTR_LIVE];
+      maxgroup = ctx->h_ctrl()[CTR_MAXGROUP];
+      list_nr = out_nr;
+      list_id = out_id;
+      after_seg = true;
+      h *= 2;
+      continue;
+    }
+
+    if (after_seg) {  // group sizes never grow, so a segmented round is never followed by a global sort
+      set_err(ctx->err, "internal: global sort requested after a segmented round (maxgroup %u)", maxgroup);
+      return BWTC_CUDA_EINTERNAL;
+    }
+    // ---- global radix round
     const bool from_list = ((uint64_t)m * 8 <= (uint64_t)N);
+    if (from_list && !have_lists && make_lists()) return BWTC_CUDA_ECUDA;
     if (zero_round_state(ctx, N, m, RS_TILE64, maskd)) return BWTC_CUDA_ECUDA;
     if (from_list) {
-      // few live suffixes: gather-build from the list into the (dead) buffer that held the sorted records
+      // few live suffixes: gather-build from the id list (in d_keys[cur]) into the other buffer pair
+      const int tb = cur ^ 1;
       const uint32_t bt = div_up(m, 256);
       const int grid = (int)(bt < (uint32_t)(ctx->sm_count * 8) ? bt : (uint32_t)(ctx->sm_count * 8));
-      k_build_from_list<<<grid, 256, 0, st>>>(live_list, m, ctx->d_rank, N, h32, lo_bits,
-                                              static_cast<unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur],
+      k_build_from_list<<<grid, 256, 0, st>>>(pool[list_id], m, ctx->d_rank, N, h32, lo_bits,
+                                              static_cast<unsigned long long*>(ctx->d_keys[tb]), ctx->d_idx[tb],
                                               ctx->d_hist(), (int)npassd);
       CK(ctx, cudaGetLastError());
       S.kernel_launches++;
       S.algorithmic_bytes += (uint64_t)m * (4 + 8 + 12);
+      cur = tb;
     } else {
       const uint32_t btiles = div_up(N, AUX_TILE);
       const int grid = (int)(btiles < (uint32_t)(ctx->sm_count * 8) ? btiles : (uint32_t)(ctx->sm_count * 8));
@@ -516,6 +587,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       S.algorithmic_bytes += (uint64_t)N * 4 + (uint64_t)m * 12;
       cur = 0;
     }
+    have_lists = false;
     rc = run_sort<unsigned long long, RS_IPT64>(ctx, m, maskd, false, 0, &cur, &pt, &pdone);
     if (rc) return rc;
     {
@@ -528,9 +600,10 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
         rp.win_lo = (uint32_t)((uint64_t)N * w / nwin);
         rp.win_hi = (uint32_t)((uint64_t)N * (w + 1) / nwin);
         rp.ctr_slot = CTR_RERANK + w;
+        StageParams sp{pool[2 * (cur ^ 1)], pool[2 * (cur ^ 1) + 1], ctx->d_tilecnt, w == 0 ? 1 : 0};
         k_rerank<unsigned long long, false><<<div_up(m, AUX_TILE), 256, 0, st>>>(
             static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp,
-            ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl(), ep, ctx->d_idx[cur ^ 1]);
+            ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl(), ep, sp);
         CK(ctx, cudaGetLastError());
         S.kernel_launches++;
       }
@@ -551,6 +624,8 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     S.prefix_len[r] = h32;
     S.rounds = r + 1;
     live = ctx->h_ctrl()[CTR_LIVE];
+    maxgroup = ctx->h_ctrl()[CTR_MAXGROUP];
+    m_prev = m;
     ctx->last_cur = cur;
     h *= 2;
   }
@@ -627,6 +702,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (!c) { set_err(g_err, "out of host memory"); return BWTC_CUDA_EALLOC; }
   c->device = device;
   c->cap = max_block_bytes;
+  if (const char* e = getenv("BWTC_SEG")) c->use_seg = atoi(e);
   if (const char* e = getenv("BWTC_RERANK_WINDOW_MB")) { long v = atol(e); if (v > 0) c->rerank_window_bytes = (uint64_t)v << 20; }
   c->err[0] = 0;
   memset(&c->stats, 0, sizeof(c->stats));
@@ -662,6 +738,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_status, (size_t)MAX_PASSES * c->max_rs_tiles * 1024u);
   ALLOC(c->d_LF, (256 + 8) * 4);
   ALLOC(c->d_wtab, (size_t)WS_SLOTS * 12 + 64);
+  ALLOC(c->d_tilecnt, (size_t)c->max_aux_tiles * 8 + 64);
 #undef ALLOC
   if (!rc) {
     e = cudaMallocHost((void**)&c->h_small, (size_t)(CTR_WORDS + HIST_WORDS + 256 + 8) * 4);

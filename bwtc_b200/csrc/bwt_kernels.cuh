@@ -30,6 +30,8 @@ constexpr int CTR_RERANK = 32;     // [32..47] dynamic tile counters of the k_re
 constexpr int MAX_RERANK_WINDOWS = 16;
 constexpr int CTR_CURSOR = 17;     // output cursor of k_build_keys (== number of live records emitted)
 constexpr int CTR_LIVE = 18;       // records still in non-singleton groups after k_rerank
+constexpr int CTR_UPD = 21;        // cursor of the rank-update list written by k_seg_round
+constexpr int CTR_MAXGROUP = 20;   // size of the largest non-singleton group seen by the re-rank of this round
 constexpr int CTR_ERR = 19;        // != 0: a look-back watchdog fired (engine returns BWTC_CUDA_EINTERNAL)
 constexpr int CTR_WORDS = 64;
 
@@ -709,6 +711,18 @@ struct RerankParams {
   uint32_t ctr_slot;        // ctrl word used as the dynamic tile counter of this launch
 };
 
+// Live-record staging of k_rerank.  The window launch with sp.enable != 0 writes, for EVERY record of its tile
+// that stays in a non-singleton group (whatever its id window), the pair (new rank, id) in sorted order to
+// stage_*[tile_base + 0 .. cnt) and the count to tile_cnt[tile]; it also owns ctrl[CTR_LIVE] / [CTR_MAXGROUP].
+// k_scan_tile_counts + k_gather_chunks later concatenate the chunks — in tile order, so every group stays
+// contiguous — into the compact lists that k_seg_round, k_small_rounds and k_build_from_list consume.
+struct StageParams {
+  uint32_t* stage_nr;
+  uint32_t* stage_id;
+  uint32_t* tile_cnt;
+  int enable;
+};
+
 // BWT emission fused into the re-rank: the moment a suffix becomes a singleton its rank is final, the records
 // are at hand in SORTED order, so L[rank] = T[id-1] is written with (nearly) consecutive addresses and only the
 // text gather (L2-resident) is random.  No separate N-element byte scatter remains.  The one byte that the block
@@ -725,18 +739,16 @@ template <typename KeyT, bool ROUND0>
 __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx,
                                                 uint32_t* __restrict__ rank, RerankParams rp,
                                                 unsigned long long* __restrict__ tstate,
-                                                uint32_t* __restrict__ ctrl, EmitParams ep,
-                                                uint32_t* __restrict__ live_out) {
+                                                uint32_t* __restrict__ ctrl, EmitParams ep, StageParams sp) {
   constexpr int BLOCK = 256, IPT = 8, TILE = BLOCK * IPT, WARPS = BLOCK / 32;
   __shared__ KeyT s_lastkey[BLOCK];
   __shared__ uint32_t s_lastshort[BLOCK];
   __shared__ uint32_t s_firsthead[BLOCK + 1];
   __shared__ uint32_t s_wf[WARPS], s_wh[WARPS];
-  __shared__ uint32_t s_tile, s_cf, s_ch, s_live, s_firsth0;
+  __shared__ uint32_t s_tile, s_cf, s_ch, s_firsth0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     s_tile = atomicAdd(&ctrl[rp.ctr_slot], 1u);
-    s_live = 0;
   }
   __syncthreads();
   const uint32_t tile = s_tile;
@@ -913,10 +925,11 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
   exh = max(exh, s_ch);
   const uint32_t nexthead_thread = s_firsthead[tid + 1];
 
-  uint32_t live = 0, livemask = 0;
+  uint32_t live = 0, livemask = 0, gmax = 0, stnr[IPT];
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
     const uint32_t j = j0 + k;
+    stnr[k] = 0;
     if (j < m) {
       const uint32_t HF = max(lf[k], exf) - 1u;  // >= 0: record 0 is always a head
       const bool hf = (headfull >> k) & 1u;
@@ -938,21 +951,24 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
         if (ep.block_mode && nr == ep.N - 1) *ep.lastch = 0x100u | ch;
         else ep.out[nr] = ch;
       }
-      if (single) nr |= RANK_DONE; else if (in_win) { ++live; livemask |= 1u << k; }
+      if (single) nr |= RANK_DONE;
+      else if (sp.enable) { ++live; livemask |= 1u << k; gmax = max(gmax, j - HF + 1u); stnr[k] = nr; }
       if (in_win && (changed || single)) rank[id[k]] = nr;
     }
   }
-  // The ids still in non-singleton groups are appended to live_out (any order): ctrl[CTR_LIVE] is both the
-  // live count the host reads and the append cursor (one global atomic per tile).  Small next rounds are built
-  // from this list instead of a scan over all N ranks.
+  if (!sp.enable) return;
+  // ---- stage the records that stay live: (new rank, id) in sorted order at the start of this tile's slot
   uint32_t inc = live;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
     if (lane >= o) inc += t;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
   __syncthreads();  // s_wf is free again
   if (lane == 31) s_wf[warp] = inc;
+  if (lane == 0 && gmax) atomicMax(&ctrl[CTR_MAXGROUP], gmax);
   __syncthreads();
   uint32_t woff = 0, total = 0;
 #pragma unroll
@@ -961,13 +977,64 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
     if (w < warp) woff += t;
     total += t;
   }
-  if (tid == 0) s_live = total ? atomicAdd(&ctrl[CTR_LIVE], total) : 0u;
-  __syncthreads();
-  if (live_out != nullptr && live) {
-    uint32_t pos = s_live + woff + inc - live;
+  if (tid == 0) {
+    sp.tile_cnt[tile] = total;
+    if (total) atomicAdd(&ctrl[CTR_LIVE], total);
+  }
+  if (live) {
+    uint32_t pos = tile_base + woff + inc - live;
 #pragma unroll
-    for (int k = 0; k < IPT; ++k)
-      if ((livemask >> k) & 1u) live_out[pos++] = id[k];
+    for (int k = 0; k < IPT; ++k) {
+      if ((livemask >> k) & 1u) {
+        sp.stage_nr[pos] = stnr[k];
+        sp.stage_id[pos] = id[k];
+        ++pos;
+      }
+    }
+  }
+}
+
+// k_scan_tile_counts (one CTA): exclusive prefix of the per-tile live counts.  k_gather_chunks: tile t copies its
+// staged chunk to out[excl[t] ..) — the concatenation keeps the sorted order, so groups stay contiguous.
+__global__ void __launch_bounds__(1024) k_scan_tile_counts(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ excl,
+                                                           uint32_t ntiles) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < ntiles; base += 1024) {
+    const uint32_t i = base + tid;
+    const uint32_t v = (i < ntiles) ? cnt[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+    for (int w = 0; w < 32; ++w) { const uint32_t t = s_w[w]; if (w < warp) woff += t; total += t; }
+    const uint32_t carry = s_carry;
+    if (i < ntiles) excl[i] = carry + woff + inc - v;
+    __syncthreads();
+    if (tid == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gather_chunks(const uint32_t* __restrict__ stage_nr,
+                                                       const uint32_t* __restrict__ stage_id,
+                                                       const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ excl,
+                                                       uint32_t tile_records, uint32_t* __restrict__ out_nr,
+                                                       uint32_t* __restrict__ out_id) {
+  const uint32_t tile = blockIdx.x;
+  const uint32_t c = cnt[tile], dst = excl[tile];
+  const size_t src = (size_t)tile * tile_records;
+  for (uint32_t t = threadIdx.x; t < c; t += blockDim.x) {
+    out_nr[dst + t] = stage_nr[src + t];
+    out_id[dst + t] = stage_id[src + t];
   }
 }
 
@@ -1000,6 +1067,256 @@ __global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restr
     const uint32_t v = s_hist[p * 256 + tid];
     if (v) atomicAdd(&hist[p * 256 + tid], v);
   }
+}
+
+// =====================================================================================================
+// k_seg_round — one doubling round WITHOUT a global sort, for rounds whose groups are all small.
+// After any round the still-live records sit in rank order with every group contiguous, so the next round only
+// has to order each group by rank[i+h]: a tile of ~1920 records, extended to the next group boundary on both
+// sides (groups are <= SEG_MAXGROUP long, checked by the host from ctrl[CTR_MAXGROUP]), has each of its groups
+// ordered by (old rank, rank[i+h]) by counting inside the group in shared memory, is re-ranked, its new singletons are emitted, and
+// the records still tied are appended — whole groups at a time, in order — as the input of the next round.
+// One kernel replaces key build + 7 digit passes + re-rank (~0.45 ms for the 2.6 M live suffixes of the Markov
+// block's second round).  Input may contain holes (RANK_DONE records of the previous global sort).
+// Replaces tr_introsort over small groups (trsort.c:327-552).
+// =====================================================================================================
+constexpr int SEG_T = 1920, SEG_CAP = 2048, SEG_MAXGROUP = 128;
+
+__global__ void __launch_bounds__(256) k_seg_round(const uint32_t* __restrict__ nr_in, const uint32_t* __restrict__ id_in,
+                                                   uint32_t m_in, const uint32_t* __restrict__ rank, uint32_t N,
+                                                   uint32_t h, EmitParams ep, uint32_t* __restrict__ nr_out,
+                                                   uint32_t* __restrict__ id_out, uint32_t* __restrict__ upd_id,
+                                                   uint32_t* __restrict__ upd_nr, uint32_t* __restrict__ ctrl) {
+  constexpr int IPT = SEG_CAP / 256;
+  __shared__ unsigned long long s_key[SEG_CAP];
+  __shared__ uint32_t s_id[SEG_CAP];
+  __shared__ uint32_t s_wa[8], s_wb[8];
+  __shared__ uint32_t s_start, s_end, s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t a = blockIdx.x * (uint32_t)SEG_T;
+  if (a >= m_in) return;
+  const uint32_t b = (m_in - a > (uint32_t)SEG_T) ? a + SEG_T : m_in;
+  if (tid == 0) { s_start = 0xFFFFFFFFu; s_end = (b >= m_in) ? m_in : 0xFFFFFFFFu; }
+  __syncthreads();
+  // ---- extend the tile to group boundaries: first group head at or after a, first group head at or after b
+  for (uint32_t t = tid; t <= (uint32_t)SEG_MAXGROUP; t += 256) {
+    const uint32_t ja = a + t;
+    if (ja < m_in) {
+      if (ja == 0 || nr_in[ja] != nr_in[ja - 1]) atomicMin(&s_start, ja);
+    } else if (ja == m_in) {
+      atomicMin(&s_start, m_in);
+    }
+    const uint32_t jb = b + t;
+    if (b < m_in) {
+      if (jb < m_in) {
+        if (nr_in[jb] != nr_in[jb - 1]) atomicMin(&s_end, jb);
+      } else if (jb == m_in) {
+        atomicMin(&s_end, m_in);
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t start = s_start, end = s_end;
+  if (start == 0xFFFFFFFFu || end == 0xFFFFFFFFu || (start < end && end - start > (uint32_t)SEG_CAP)) {
+    if (tid == 0) atomicExch(&ctrl[CTR_ERR], 4u);  // a group longer than SEG_MAXGROUP: the host must not pick this path
+    return;
+  }
+  if (start >= end) return;
+  // ---- load my records (thread-blocked, order preserved), drop the holes, build (old rank, rank[i+h]) keys
+  uint32_t myid[IPT], mynr[IPT];
+  uint32_t livemask = 0;
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t j = start + tid * IPT + k;
+    mynr[k] = RANK_DONE;
+    myid[k] = 0;
+    if (j < end) { mynr[k] = nr_in[j]; myid[k] = id_in[j]; }
+    if (!(mynr[k] & RANK_DONE)) livemask |= 1u << k;
+  }
+  uint32_t cnt = __popc(livemask), inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_wa[warp] = inc;
+  __syncthreads();
+  uint32_t woff = 0, L = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { const uint32_t t = s_wa[w]; if (w < warp) woff += t; L += t; }
+  {
+    uint32_t lo[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {  // independent gathers first (all in flight together), shared-memory writes after
+      lo[k] = 0;
+      if (((livemask >> k) & 1u) && h < N - myid[k]) lo[k] = (rank[myid[k] + h] & RANK_MASK) + 1u;
+    }
+    uint32_t pos = woff + inc - cnt;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      if ((livemask >> k) & 1u) {
+        s_key[pos] = ((unsigned long long)mynr[k] << 32) | lo[k];
+        s_id[pos] = myid[k];
+        ++pos;
+      }
+    }
+  }
+  __syncthreads();
+  if (L == 0) return;
+  const uint32_t P = L;
+  // ---- order every group by counting: the records are already grouped by old rank, groups are short
+  // (<= SEG_MAXGROUP), so each record just counts the members of its own group that precede it.  No sorting
+  // network: a full bitonic sort of the tile was measured 8x slower (374 us for 2.6 M records).
+  {
+    unsigned long long kreg[IPT];
+    uint32_t ireg[IPT], npos[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t j = tid * IPT + k;
+      npos[k] = 0xFFFFFFFFu;
+      if (j < L) {
+        kreg[k] = s_key[j];
+        ireg[k] = s_id[j];
+        const uint32_t g = (uint32_t)(kreg[k] >> 32);
+        uint32_t cntb = 0, gs = j;
+        for (uint32_t q = j; q-- > 0;) {
+          const unsigned long long kq = s_key[q];
+          if ((uint32_t)(kq >> 32) != g) break;
+          cntb += (kq <= kreg[k]) ? 1u : 0u;
+          gs = q;
+        }
+        for (uint32_t q = j + 1; q < L; ++q) {
+          const unsigned long long kq = s_key[q];
+          if ((uint32_t)(kq >> 32) != g) break;
+          cntb += (kq < kreg[k]) ? 1u : 0u;
+        }
+        npos[k] = gs + cntb;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      if (npos[k] != 0xFFFFFFFFu) {
+        s_key[npos[k]] = kreg[k];
+        s_id[npos[k]] = ireg[k];
+      }
+    }
+    __syncthreads();
+  }
+  // ---- re-rank inside the tile (it starts and ends on group boundaries: no carry from other tiles)
+  unsigned long long key[IPT];
+  uint32_t runf = 0, runh = 0, lf[IPT], lh[IPT], hfmask = 0;
+  const uint32_t j0 = tid * IPT;
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t j = j0 + k;
+    key[k] = (j < P) ? s_key[j] : ~0ull;
+    myid[k] = (j < P) ? s_id[j] : 0u;
+    const unsigned long long pk = (j > 0 && j <= P) ? s_key[j - 1] : 0ull;
+    const bool hf = (j == 0) || (j >= L) || (key[k] != pk);
+    const bool hh = (j == 0) || (j >= L) || ((key[k] >> 32) != (pk >> 32));
+    if (hf) { hfmask |= 1u << k; runf = j + 1; }
+    if (hh) runh = j + 1;
+    lf[k] = runf;
+    lh[k] = runh;
+  }
+  const unsigned long long nextkey = (j0 + IPT < P) ? s_key[j0 + IPT] : ~0ull;
+  uint32_t incf = runf, inch = runh;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t tf = __shfl_up_sync(0xFFFFFFFFu, incf, o), th = __shfl_up_sync(0xFFFFFFFFu, inch, o);
+    if (lane >= o) { incf = max(incf, tf); inch = max(inch, th); }
+  }
+  uint32_t exf = __shfl_up_sync(0xFFFFFFFFu, incf, 1), exh = __shfl_up_sync(0xFFFFFFFFu, inch, 1);
+  if (lane == 0) { exf = 0; exh = 0; }
+  __syncthreads();  // everyone has read s_key / s_id into registers
+  if (lane == 31) { s_wa[warp] = incf; s_wb[warp] = inch; }
+  __syncthreads();
+  for (int w = 0; w < warp; ++w) { exf = max(exf, s_wa[w]); exh = max(exh, s_wb[w]); }
+  // NOTE: rank[] is NOT written here.  Other CTAs are still reading rank[i+h] of this round; a half-refined
+  // rank[] could order two members of one group by ranks of different generations.  Changed ranks go to an
+  // update list that k_apply_ranks scatters after this kernel.
+  uint32_t keep = 0, updm = 0, newnr[IPT], gmax = 0;
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const uint32_t j = j0 + k;
+    newnr[k] = 0;
+    if (j < L) {
+      const uint32_t HF = max(lf[k], exf) - 1u, HH = max(lh[k], exh) - 1u;
+      const unsigned long long nk = (k == IPT - 1) ? nextkey : key[k + 1];
+      const bool single = ((hfmask >> k) & 1u) && (j + 1 >= L || nk != key[k]);
+      uint32_t nr = (uint32_t)(key[k] >> 32) + (HF - HH);
+      if (single && myid[k] > 0) {
+        const uint8_t ch = ep.text[myid[k] - 1];
+        if (ep.block_mode && nr == ep.N - 1) *ep.lastch = 0x100u | ch;
+        else ep.out[nr] = ch;
+      }
+      if (single) nr |= RANK_DONE; else { keep |= 1u << k; gmax = max(gmax, j - HF + 1u); }
+      newnr[k] = nr;
+      if (single || HF != HH) updm |= 1u << k;
+    }
+  }
+  // ---- append the records still tied (whole groups, in order) for the next round, and the rank updates
+  cnt = __popc(keep);
+  inc = cnt;
+  const uint32_t ucnt = __popc(updm);
+  uint32_t uinc = ucnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    const uint32_t tu = __shfl_up_sync(0xFFFFFFFFu, uinc, o);
+    if (lane >= o) { inc += t; uinc += tu; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
+  __syncthreads();
+  if (lane == 31) { s_wa[warp] = inc; s_wb[warp] = uinc; }
+  if (lane == 0 && gmax) atomicMax(&ctrl[CTR_MAXGROUP], gmax);
+  __syncthreads();
+  woff = 0;
+  uint32_t total = 0, uoff = 0, utotal = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const uint32_t t = s_wa[w], tu = s_wb[w];
+    if (w < warp) { woff += t; uoff += tu; }
+    total += t;
+    utotal += tu;
+  }
+  if (tid == 0) {
+    s_base = total ? atomicAdd(&ctrl[CTR_LIVE], total) : 0u;
+    s_start = utotal ? atomicAdd(&ctrl[CTR_UPD], utotal) : 0u;  // s_start is free again
+  }
+  __syncthreads();
+  if (cnt) {
+    uint32_t pos = s_base + woff + inc - cnt;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      if ((keep >> k) & 1u) {
+        nr_out[pos] = newnr[k];
+        id_out[pos] = myid[k];
+        ++pos;
+      }
+    }
+  }
+  if (ucnt) {
+    uint32_t pos = s_start + uoff + uinc - ucnt;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      if ((updm >> k) & 1u) {
+        upd_id[pos] = myid[k];
+        upd_nr[pos] = newnr[k];
+        ++pos;
+      }
+    }
+  }
+}
+
+// k_apply_ranks — second half of a segmented round: rank[id] = new rank for every record whose rank changed or
+// became final.  The count is read from ctrl[CTR_UPD] on the device (no host round trip in between).
+__global__ void __launch_bounds__(256) k_apply_ranks(const uint32_t* __restrict__ upd_id, const uint32_t* __restrict__ upd_nr,
+                                                     const uint32_t* __restrict__ ctrl, uint32_t* __restrict__ rank) {
+  const uint32_t n = ctrl[CTR_UPD];
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) rank[upd_id[j]] = upd_nr[j];
 }
 
 // =====================================================================================================
