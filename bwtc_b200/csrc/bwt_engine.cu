@@ -5,6 +5,7 @@
 #include "../../include/bwtc_cuda.h"
 #include "bwt_kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -62,7 +63,10 @@ struct bwtc_cuda_ctx {
   uint32_t* d_zero = nullptr;  // [ctrl CTR_WORDS][hist HIST_WORDS][tstate 2*max_aux_tiles] zeroed per round
   uint32_t* d_status = nullptr;  // [MAX_PASSES][max_rs_tiles][256]
   uint32_t* d_LF = nullptr;
-  uint32_t* d_tilecnt = nullptr;  // [2][max_aux_tiles]: per-tile live counts of k_rerank and their exclusive prefix
+  uint32_t* d_tilecnt = nullptr;  // [2][max_aux_tiles]: per-tile live counts of k_rerank and their exclusive prefix,
+                                  // then [max_aux_tiles][MAX_RERANK_WINDOWS+1] bucket offsets of the bucketed scatter
+  uint32_t* d_scat = nullptr;     // u32[N]: staged ranks of the bucketed scatter (the ids go to the idle id buffer)
+  int bucket_min_windows = 3;     // bucketed scatter from this many L2 windows on (0 = never)
   unsigned long long* d_wtab = nullptr;  // window-sample table: WS_SLOTS keys, WS_SLOTS counters, 2 doubles
   size_t max_rs_tiles = 0, max_aux_tiles = 0;
   // pinned host
@@ -110,7 +114,7 @@ void ctx_free(bwtc_cuda_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_in); cudaFree(c->d_text); cudaFree(c->d_out); cudaFree(c->d_rank);
   cudaFree(c->d_keys[0]); cudaFree(c->d_keys[1]); cudaFree(c->d_idx[0]); cudaFree(c->d_idx[1]);
-  cudaFree(c->d_zero); cudaFree(c->d_status); cudaFree(c->d_LF); cudaFree(c->d_wtab); cudaFree(c->d_tilecnt);
+  cudaFree(c->d_zero); cudaFree(c->d_status); cudaFree(c->d_LF); cudaFree(c->d_wtab); cudaFree(c->d_tilecnt); cudaFree(c->d_scat);
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -196,9 +200,15 @@ uint32_t rerank_windows(const bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m) {
   if ((uint64_t)m * 4 < (uint64_t)N) return 1;  // few scattered writes: a second read of the records costs more
   uint64_t w = ((uint64_t)N * 4 + ctx->rerank_window_bytes - 1) / ctx->rerank_window_bytes;
   if (w < 1) w = 1;
-  if (w > 8) w = 8;  // measured (256 MiB block): beyond 8 windows the re-reads cost more than the L2 residency saves
+  if (!ctx->bucket_min_windows && w > 8) w = 8;  // per-window re-reads: beyond 8 they cost more than the L2 residency saves
   if (w > MAX_RERANK_WINDOWS) w = MAX_RERANK_WINDOWS;
   return (uint32_t)w;
+}
+
+// Number of k_rerank launches (= look-back word rows to zero): one in bucket mode, else one per window.
+uint32_t rerank_launches(const bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m) {
+  const uint32_t w = rerank_windows(ctx, N, m);
+  return (ctx->bucket_min_windows && w >= (uint32_t)ctx->bucket_min_windows) ? 1u : w;
 }
 
 struct PassTimer {
@@ -262,11 +272,55 @@ int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota
 
 int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m, uint32_t rs_tile, uint32_t pass_mask) {
   const uint32_t aux_tiles = div_up(m, AUX_TILE);
-  CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)rerank_windows(ctx, N, m) * ctx->max_aux_tiles * 8, ctx->stream));
+  CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)rerank_launches(ctx, N, m) * ctx->max_aux_tiles * 8, ctx->stream));
   const uint32_t tiles = div_up(m, rs_tile);
   for (int p = 0; p < MAX_PASSES; ++p)
     if ((pass_mask >> p) & 1u)
       CK(ctx, cudaMemsetAsync(ctx->d_status + (size_t)p * ctx->max_rs_tiles * 256u, 0, (size_t)tiles * 1024u, ctx->stream));
+  return 0;
+}
+
+// k_rerank over the m sorted records in buffer `cur`, plus the rank scatter.  A rank[] array that needs three or
+// more L2 windows is written bucket by bucket (ONE k_rerank launch stages (id, rank) pairs per id bucket, one
+// k_scatter_bucket launch per bucket reads them back); with two windows re-running k_rerank per window is
+// as fast (measured) and needs no staging.
+template <typename KeyT, bool ROUND0>
+int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankParams rp, const EmitParams& ep,
+                  uint32_t* stage_nr, uint32_t* stage_id) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t tiles = div_up(m, AUX_TILE);
+  const uint32_t nwin = rerank_windows(ctx, N, m);
+  const KeyT* keys = static_cast<const KeyT*>(ctx->d_keys[cur]);
+  uint32_t* woff = ctx->d_tilecnt + 2 * ctx->max_aux_tiles;
+  if (ctx->bucket_min_windows && nwin >= (uint32_t)ctx->bucket_min_windows) {
+    const uint32_t win_ids = div_up(N, nwin);
+    rp.win_lo = 0;
+    rp.win_hi = 0xFFFFFFFFu;
+    rp.ctr_slot = CTR_RERANK;
+    rp.nbuckets = nwin;
+    rp.bucket_magic = (uint32_t)(((1ull << 32) + win_ids - 1) / win_ids);
+    StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, 1, ctx->d_idx[cur ^ 1], ctx->d_scat, woff};
+    k_rerank<KeyT, ROUND0><<<tiles, 256, 0, st>>>(keys, ctx->d_idx[cur], ctx->d_rank, rp, ctx->d_tstate(), ctx->d_ctrl(), ep, sp);
+    const uint32_t grid = std::min<uint32_t>(div_up(tiles, 8), (uint32_t)ctx->sm_count * 8u);
+    for (uint32_t b = 0; b < nwin; ++b)
+      k_scatter_bucket<<<grid, 256, 0, st>>>(ctx->d_idx[cur ^ 1], ctx->d_scat, woff, tiles, nwin, b, AUX_TILE, ctx->d_rank);
+    CK(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 1 + nwin;
+    ctx->stats.algorithmic_bytes += (uint64_t)m * 16;  // staged (id, rank) pairs: written once, read once
+    return 0;
+  }
+  for (uint32_t w = 0; w < nwin; ++w) {
+    rp.win_lo = (uint32_t)((uint64_t)N * w / nwin);
+    rp.win_hi = (w + 1 == nwin) ? 0xFFFFFFFFu : (uint32_t)((uint64_t)N * (w + 1) / nwin);
+    rp.ctr_slot = CTR_RERANK + w;
+    rp.nbuckets = 0;
+    rp.bucket_magic = 0;
+    StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, w == 0 ? 1 : 0, nullptr, nullptr, nullptr};
+    k_rerank<KeyT, ROUND0><<<tiles, 256, 0, st>>>(keys, ctx->d_idx[cur], ctx->d_rank, rp,
+                                                   ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl(), ep, sp);
+    CK(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+  }
   return 0;
 }
 
@@ -440,24 +494,10 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       rp.short_thresh = pl.chars > text_end ? 0u : text_end - pl.chars + 1u;
     }
     rp.lo_bits = 0;
-    const uint32_t tiles = div_up(N, AUX_TILE);
-    const uint32_t nwin = rerank_windows(ctx, N, N);
-    for (uint32_t w = 0; w < nwin; ++w) {
-      rp.win_lo = (uint32_t)((uint64_t)N * w / nwin);
-      rp.win_hi = (uint32_t)((uint64_t)N * (w + 1) / nwin);
-      rp.ctr_slot = CTR_RERANK + w;
-      unsigned long long* ts = ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles;
-      StageParams sp{reinterpret_cast<uint32_t*>(ctx->d_keys[cur ^ 1]), reinterpret_cast<uint32_t*>(ctx->d_keys[cur ^ 1]) + N,
-                     ctx->d_tilecnt, w == 0 ? 1 : 0};
-      if (pl.keybytes == 4)
-        k_rerank<uint32_t, true><<<tiles, 256, 0, st>>>(static_cast<const uint32_t*>(ctx->d_keys[cur]), ctx->d_idx[cur],
-                                                        ctx->d_rank, rp, ts, ctx->d_ctrl(), ep, sp);
-      else
-        k_rerank<unsigned long long, true><<<tiles, 256, 0, st>>>(
-            static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp, ts, ctx->d_ctrl(), ep, sp);
-      CK(ctx, cudaGetLastError());
-      S.kernel_launches++;
-    }
+    uint32_t* snr = reinterpret_cast<uint32_t*>(ctx->d_keys[cur ^ 1]);
+    if (pl.keybytes == 4) rc = launch_rerank<uint32_t, true>(ctx, cur, N, N, rp, ep, snr, snr + N);
+    else rc = launch_rerank<unsigned long long, true>(ctx, cur, N, N, rp, ep, snr, snr + N);
+    if (rc) return rc;
     S.algorithmic_bytes += (uint64_t)N * (pl.keybytes + 4) + (uint64_t)N * 4;
   }
   CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_WORDS * 4, cudaMemcpyDeviceToHost, st));
@@ -595,18 +635,8 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       rp.m = m;
       rp.short_thresh = 0;
       rp.lo_bits = lo_bits;
-      const uint32_t nwin = rerank_windows(ctx, N, m);
-      for (uint32_t w = 0; w < nwin; ++w) {
-        rp.win_lo = (uint32_t)((uint64_t)N * w / nwin);
-        rp.win_hi = (uint32_t)((uint64_t)N * (w + 1) / nwin);
-        rp.ctr_slot = CTR_RERANK + w;
-        StageParams sp{pool[2 * (cur ^ 1)], pool[2 * (cur ^ 1) + 1], ctx->d_tilecnt, w == 0 ? 1 : 0};
-        k_rerank<unsigned long long, false><<<div_up(m, AUX_TILE), 256, 0, st>>>(
-            static_cast<const unsigned long long*>(ctx->d_keys[cur]), ctx->d_idx[cur], ctx->d_rank, rp,
-            ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl(), ep, sp);
-        CK(ctx, cudaGetLastError());
-        S.kernel_launches++;
-      }
+      rc = launch_rerank<unsigned long long, false>(ctx, cur, m, N, rp, ep, pool[2 * (cur ^ 1)], pool[2 * (cur ^ 1) + 1]);
+      if (rc) return rc;
       S.algorithmic_bytes += (uint64_t)m * 12 + (uint64_t)m * 4;
     }
     CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_WORDS * 4, cudaMemcpyDeviceToHost, st));
@@ -703,6 +733,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   c->device = device;
   c->cap = max_block_bytes;
   if (const char* e = getenv("BWTC_SEG")) c->use_seg = atoi(e);
+  if (const char* e = getenv("BWTC_BUCKET_MIN_WINDOWS")) c->bucket_min_windows = atoi(e);
   if (const char* e = getenv("BWTC_RERANK_WINDOW_MB")) { long v = atol(e); if (v > 0) c->rerank_window_bytes = (uint64_t)v << 20; }
   c->err[0] = 0;
   memset(&c->stats, 0, sizeof(c->stats));
@@ -738,7 +769,8 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_status, (size_t)MAX_PASSES * c->max_rs_tiles * 1024u);
   ALLOC(c->d_LF, (256 + 8) * 4);
   ALLOC(c->d_wtab, (size_t)WS_SLOTS * 12 + 64);
-  ALLOC(c->d_tilecnt, (size_t)c->max_aux_tiles * 8 + 64);
+  ALLOC(c->d_tilecnt, (size_t)c->max_aux_tiles * (2 + MAX_RERANK_WINDOWS + 1) * 4 + 64);
+  ALLOC(c->d_scat, (size_t)N * 4 + 64);
 #undef ALLOC
   if (!rc) {
     e = cudaMallocHost((void**)&c->h_small, (size_t)(CTR_WORDS + HIST_WORDS + 256 + 8) * 4);

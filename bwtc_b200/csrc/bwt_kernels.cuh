@@ -709,6 +709,8 @@ struct RerankParams {
                             // scatter of a big block is split into windows that stay L2-resident (random 4-byte
                             // writes into a >L2 array cost a DRAM sector fill + write-back each)
   uint32_t ctr_slot;        // ctrl word used as the dynamic tile counter of this launch
+  uint32_t nbuckets;        // > 1: bucketed scatter — instead of writing rank[] the tile stages its (id, rank) pairs
+  uint32_t bucket_magic;    //      grouped by id bucket (bucket = min(umulhi(id, magic), nbuckets-1)); see k_scatter_bucket
 };
 
 // Live-record staging of k_rerank.  The window launch with sp.enable != 0 writes, for EVERY record of its tile
@@ -721,6 +723,12 @@ struct StageParams {
   uint32_t* stage_id;
   uint32_t* tile_cnt;
   int enable;
+  // bucketed rank scatter (RerankParams::nbuckets > 1): records of tile t, grouped by id bucket, go to
+  // sc_*[tile_base + tile_woff[t*(nbuckets+1) + b] ..); k_scatter_bucket then writes one bucket (= one L2-resident
+  // window of rank[]) per launch, reading every staged record exactly once.
+  uint32_t* sc_id;
+  uint32_t* sc_nr;
+  uint32_t* tile_woff;
 };
 
 // BWT emission fused into the re-rank: the moment a suffix becomes a singleton its rank is final, the records
@@ -746,10 +754,12 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
   __shared__ uint32_t s_firsthead[BLOCK + 1];
   __shared__ uint32_t s_wf[WARPS], s_wh[WARPS];
   __shared__ uint32_t s_tile, s_cf, s_ch, s_firsth0;
+  __shared__ uint32_t s_bcnt[MAX_RERANK_WINDOWS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     s_tile = atomicAdd(&ctrl[rp.ctr_slot], 1u);
   }
+  if (tid <= MAX_RERANK_WINDOWS) s_bcnt[tid] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t m = rp.m;
@@ -925,11 +935,14 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
   exh = max(exh, s_ch);
   const uint32_t nexthead_thread = s_firsthead[tid + 1];
 
-  uint32_t live = 0, livemask = 0, gmax = 0, stnr[IPT];
+  const bool bucketed = rp.nbuckets > 1;
+  uint32_t live = 0, livemask = 0, gmax = 0, nrv[IPT];
+  uint32_t wrmask = 0, bpos[IPT];
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
     const uint32_t j = j0 + k;
-    stnr[k] = 0;
+    nrv[k] = 0;
+    bpos[k] = 0;
     if (j < m) {
       const uint32_t HF = max(lf[k], exf) - 1u;  // >= 0: record 0 is always a head
       const bool hf = (headfull >> k) & 1u;
@@ -952,8 +965,41 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
         else ep.out[nr] = ch;
       }
       if (single) nr |= RANK_DONE;
-      else if (sp.enable) { ++live; livemask |= 1u << k; gmax = max(gmax, j - HF + 1u); stnr[k] = nr; }
-      if (in_win && (changed || single)) rank[id[k]] = nr;
+      else if (sp.enable) { ++live; livemask |= 1u << k; gmax = max(gmax, j - HF + 1u); }
+      nrv[k] = nr;
+      if (in_win && (changed || single)) {
+        if (bucketed) {
+          const uint32_t b = min(__umulhi(id[k], rp.bucket_magic), rp.nbuckets - 1u);
+          bpos[k] = atomicAdd(&s_bcnt[b], 1u);
+          wrmask |= 1u << k;
+        } else {
+          rank[id[k]] = nr;
+        }
+      }
+    }
+  }
+  if (bucketed) {
+    __syncthreads();
+    if (tid == 0) {  // exclusive starts of the buckets inside this tile's slot
+      uint32_t acc = 0;
+      uint32_t* wo = sp.tile_woff + (size_t)tile * (rp.nbuckets + 1u);
+      for (uint32_t b = 0; b < rp.nbuckets; ++b) {
+        const uint32_t c = s_bcnt[b];
+        s_bcnt[b] = acc;
+        wo[b] = acc;
+        acc += c;
+      }
+      wo[rp.nbuckets] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      if ((wrmask >> k) & 1u) {
+        const uint32_t b = min(__umulhi(id[k], rp.bucket_magic), rp.nbuckets - 1u);
+        const uint32_t dst = tile_base + s_bcnt[b] + bpos[k];
+        sp.sc_id[dst] = id[k];
+        sp.sc_nr[dst] = nrv[k];
+      }
     }
   }
   if (!sp.enable) return;
@@ -986,11 +1032,29 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       if ((livemask >> k) & 1u) {
-        sp.stage_nr[pos] = stnr[k];
+        sp.stage_nr[pos] = nrv[k];
         sp.stage_id[pos] = id[k];
         ++pos;
       }
     }
+  }
+}
+
+// k_scatter_bucket — rank[id] = nr for the staged records of ONE id bucket (all tiles).  One warp per tile
+// segment; the bucket's slice of rank[] (<= ~72 MB) stays L2-resident, so the random 4-byte writes never pay a
+// DRAM sector fill + write-back, and — unlike re-running k_rerank once per window — every record is read once.
+__global__ void __launch_bounds__(256) k_scatter_bucket(const uint32_t* __restrict__ sc_id, const uint32_t* __restrict__ sc_nr,
+                                                        const uint32_t* __restrict__ tile_woff, uint32_t ntiles,
+                                                        uint32_t nbuckets, uint32_t b, uint32_t tile_records,
+                                                        uint32_t* __restrict__ rank) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t nw = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < ntiles; tile += nw) {
+    const uint32_t* wo = tile_woff + (size_t)tile * (nbuckets + 1u);
+    const uint32_t lo = wo[b], hi = wo[b + 1];
+    const size_t base = (size_t)tile * tile_records;
+#pragma unroll 4
+    for (uint32_t t = lo + lane; t < hi; t += 32) rank[__ldcs(sc_id + base + t)] = __ldcs(sc_nr + base + t);
   }
 }
 

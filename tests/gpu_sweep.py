@@ -2,6 +2,7 @@
 """tests/gpu_sweep.py — perf probes on a GPU box (not a pytest).
   python tests/gpu_sweep.py one  KIND MIB [chars keybytes]      one block (for ncu launch lists)
   python tests/gpu_sweep.py sweep                                round-0 key-shape sweep per input family
+  python tests/gpu_sweep.py configs                              one block of each BASELINE config (REPS=1 under ncu)
 """
 import os
 import sys
@@ -37,6 +38,24 @@ def main():
         ctx.set_timing(1)
         st = run(ctx, x, reps=int(os.environ.get("REPS", "1")))
         print(st)
+    elif mode == "configs":
+        reps = int(os.environ.get("REPS", "3"))
+        cfgs = (("markov", 1), ("dna", 64), ("repetitive", 16), ("random", 256), ("markov", 32))
+        if os.environ.get("CONFIGS"):
+            cfgs = tuple((c.split(":")[0], int(c.split(":")[1])) for c in os.environ["CONFIGS"].split(","))
+        for kind, mib in cfgs:
+            n = mib << 20
+            ctx = bw.CudaContext(n)
+            ctx.set_timing(1)
+            x = bw.generate(kind, n, seed=5)
+            st = run(ctx, x, reps=reps)
+            r = st["rounds"]
+            print(f"CONFIG {kind:10s} {mib:4d}MiB c={st['chars_round0']} keyB={st['key_bytes_round0']} rounds={r} "
+                  f"live/N={[round(v / st['n_suffixes'], 4) for v in st['live'][:r]]} passes={st['passes'][:r]} "
+                  f"launches={st['kernel_launches']} B_alg={st['algorithmic_bytes']} gpu_ms={st['gpu_ms']:.3f} "
+                  f"MB/s={n / 1e6 / (st['gpu_ms'] / 1e3):.0f} B_alg/t={st['algorithmic_bytes'] / 1e9 / (st['gpu_ms'] / 1e3):.0f}GB/s",
+                  flush=True)
+            ctx.close()
     else:
         sizes = [int(s) for s in os.environ.get("MIBS", "32").split(",")]
         for kind in os.environ.get("KINDS", "markov,dna,repetitive,random").split(","):
