@@ -66,6 +66,7 @@ struct bwtc_cuda_ctx {
   uint32_t* d_tilecnt = nullptr;  // [2][max_aux_tiles]: per-tile live counts of k_rerank and their exclusive prefix,
                                   // then [max_aux_tiles][MAX_RERANK_WINDOWS+1] bucket offsets of the bucketed scatter
   uint32_t* d_scat = nullptr;     // u32[N]: staged ranks of the bucketed scatter (the ids go to the idle id buffer)
+  int use_pack_pred = 1;          // carry code(T[id-1]) above the id through the round-0 sort when it fits
   int bucket_min_windows = 3;     // bucketed scatter from this many L2 windows on (0 = never)
   unsigned long long* d_wtab = nullptr;  // window-sample table: WS_SLOTS keys, WS_SLOTS counters, 2 doubles
   size_t max_rs_tiles = 0, max_aux_tiles = 0;
@@ -233,7 +234,7 @@ struct PassTimer {
 // between buffer 0 and 1.  Records start in buffer `cur` (0); returns the buffer holding the result.
 template <typename KeyT, int IPT>
 int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota, uint32_t iota_top, int* cur_io,
-             PassTimer* pt, uint32_t* passes_done) {
+             PassTimer* pt, uint32_t* passes_done, uint32_t pack_bits = 0, uint32_t topshift = 0) {
   constexpr uint32_t TILE = RS_BLOCK * IPT;
   const uint32_t tiles = div_up(m, TILE);
   const size_t smem = RadixPassSmem<KeyT, RS_BLOCK, IPT>::bytes;
@@ -249,11 +250,11 @@ int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota
     if (iota)
       k_radix_pass<KeyT, RS_BLOCK, IPT, true><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-          CTR_PASS0 + p, iota_top);
+          CTR_PASS0 + p, iota_top, pack_bits, topshift);
     else
       k_radix_pass<KeyT, RS_BLOCK, IPT, false><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, ctx->d_idx[cur], kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-          CTR_PASS0 + p, iota_top);
+          CTR_PASS0 + p, iota_top, 0u, 0u);
     CK(ctx, cudaGetLastError());
     if (pt->end()) return BWTC_CUDA_ECUDA;
     ctx->stats.kernel_launches++;
@@ -476,8 +477,16 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   int cur = 0;
   uint32_t pdone = 0;
   int rc;
-  if (pl.keybytes == 4) rc = run_sort<uint32_t, RS_IPT32>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone);
-  else rc = run_sort<unsigned long long, RS_IPT64>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone);
+  // When the id and one character code fit a 32-bit payload together, the first pass stores the code of the
+  // character preceding each suffix above the id: the round-0 BWT emission then needs no text gather.
+  uint32_t id_bits = (uint32_t)ceil_log2_u64((uint64_t)N);
+  if (id_bits < 1) id_bits = 1;
+  const bool pack_pred = ctx->use_pack_pred && (id_bits + pl.bits <= 32) && (mask0 & 1u);
+  const uint32_t topshift = (pl.chars - 1) * pl.bits;
+  if (pl.keybytes == 4)
+    rc = run_sort<uint32_t, RS_IPT32>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone, pack_pred ? id_bits : 0u, topshift);
+  else
+    rc = run_sort<unsigned long long, RS_IPT64>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone, pack_pred ? id_bits : 0u, topshift);
   if (rc) return rc;
   const size_t round0_events = pt.used;
   S.sort0_launches = S.sort_launches;
@@ -494,6 +503,12 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       rp.short_thresh = pl.chars > text_end ? 0u : text_end - pl.chars + 1u;
     }
     rp.lo_bits = 0;
+    rp.packed = pack_pred ? 1u : 0u;
+    rp.id_bits = pack_pred ? id_bits : 31u;
+    rp.id_mask = pack_pred ? (uint32_t)((1ull << id_bits) - 1ull) : 0xFFFFFFFFu;
+    memset(rp.decode, 0, sizeof(rp.decode));
+    for (int c = 0; c < 256; ++c)
+      if (present[c]) rp.decode[pl.pp.lut[c]] = (uint8_t)c;
     uint32_t* snr = reinterpret_cast<uint32_t*>(ctx->d_keys[cur ^ 1]);
     if (pl.keybytes == 4) rc = launch_rerank<uint32_t, true>(ctx, cur, N, N, rp, ep, snr, snr + N);
     else rc = launch_rerank<unsigned long long, true>(ctx, cur, N, N, rp, ep, snr, snr + N);
@@ -635,6 +650,9 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       rp.m = m;
       rp.short_thresh = 0;
       rp.lo_bits = lo_bits;
+      rp.packed = 0;
+      rp.id_bits = 31;
+      rp.id_mask = 0xFFFFFFFFu;
       rc = launch_rerank<unsigned long long, false>(ctx, cur, m, N, rp, ep, pool[2 * (cur ^ 1)], pool[2 * (cur ^ 1) + 1]);
       if (rc) return rc;
       S.algorithmic_bytes += (uint64_t)m * 12 + (uint64_t)m * 4;
@@ -733,6 +751,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   c->device = device;
   c->cap = max_block_bytes;
   if (const char* e = getenv("BWTC_SEG")) c->use_seg = atoi(e);
+  if (const char* e = getenv("BWTC_PACK_PRED")) c->use_pack_pred = atoi(e);
   if (const char* e = getenv("BWTC_BUCKET_MIN_WINDOWS")) c->bucket_min_windows = atoi(e);
   if (const char* e = getenv("BWTC_RERANK_WINDOW_MB")) { long v = atol(e); if (v > 0) c->rerank_window_bytes = (uint64_t)v << 20; }
   c->err[0] = 0;

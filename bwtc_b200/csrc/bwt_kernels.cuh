@@ -500,7 +500,11 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
                                                       uint32_t n, uint32_t shift,
                                                       const uint32_t* __restrict__ ghist,
                                                       uint32_t* __restrict__ status, uint32_t* __restrict__ ctrl,
-                                                      uint32_t ctr_slot, uint32_t iota_top) {
+                                                      uint32_t ctr_slot, uint32_t iota_top, uint32_t pack_bits,
+                                                      uint32_t topshift) {
+  // IOTA: ids are generated (position g holds suffix iota_top - g).  pack_bits != 0 additionally stores, above
+  // bit pack_bits of the id, the dense code of the character PRECEDING the suffix — the top character of the
+  // next key in the array — so the BWT emission of k_rerank needs no text gather at all.
   static_assert(BLOCK >= 256 && BLOCK % 32 == 0, "BLOCK must cover the 256 digit bins");
   constexpr int TILE = BLOCK * IPT, WARPS = BLOCK / 32;
   static_assert(TILE <= 65536, "local positions are kept as uint16");
@@ -537,12 +541,21 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
     for (int k = 0; k < IPT; ++k) key[k] = keys_in[first + 32 * k];
 #pragma unroll
     for (int k = 0; k < IPT; ++k) val[k] = IOTA ? (iota_top - (first + 32 * k)) : vals_in[first + 32 * k];
+    if (IOTA && pack_bits) {
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        const uint32_t g1 = first + 32 * k + 1u;
+        const uint32_t pc = (g1 < n) ? (uint32_t)(keys_in[g1] >> topshift) : 0u;  // L1 hit: the neighbour's key
+        val[k] |= pc << pack_bits;
+      }
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       const uint32_t g = first + 32 * k;
       key[k] = (g < n) ? keys_in[g] : (KeyT)~(KeyT)0;  // pads: digit 255, last in index order
       val[k] = (g < n) ? (IOTA ? (iota_top - g) : vals_in[g]) : 0u;
+      if (IOTA && pack_bits && g + 1u < n) val[k] |= (uint32_t)(keys_in[g + 1u] >> topshift) << pack_bits;
     }
   }
 
@@ -709,6 +722,10 @@ struct RerankParams {
                             // scatter of a big block is split into windows that stay L2-resident (random 4-byte
                             // writes into a >L2 array cost a DRAM sector fill + write-back each)
   uint32_t ctr_slot;        // ctrl word used as the dynamic tile counter of this launch
+  uint32_t id_mask;         // ROUND0: the sorted payload is id | code(T[id-1]) << id_bits when packed != 0
+  uint32_t id_bits;
+  uint32_t packed;
+  uint8_t decode[256];      // dense code -> byte (packed emission)
   uint32_t nbuckets;        // > 1: bucketed scatter — instead of writing rank[] the tile stages its (id, rank) pairs
   uint32_t bucket_magic;    //      grouped by id bucket (bucket = min(umulhi(id, magic), nbuckets-1)); see k_scatter_bucket
 };
@@ -755,10 +772,12 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
   __shared__ uint32_t s_wf[WARPS], s_wh[WARPS];
   __shared__ uint32_t s_tile, s_cf, s_ch, s_firsth0;
   __shared__ uint32_t s_bcnt[MAX_RERANK_WINDOWS + 1];
+  __shared__ uint8_t s_dec[ROUND0 ? 256 : 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     s_tile = atomicAdd(&ctrl[rp.ctr_slot], 1u);
   }
+  if (ROUND0 && rp.packed) s_dec[tid] = rp.decode[tid];
   if (tid <= MAX_RERANK_WINDOWS) s_bcnt[tid] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
@@ -800,6 +819,16 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
       id[k] = (j < m) ? idx[j] : 0u;
     }
   }
+  uint32_t pc0 = 0, pc1 = 0;  // packed predecessor codes of the 8 records (one byte each)
+  if (ROUND0 && rp.packed) {
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t c = id[k] >> rp.id_bits;
+      if (k < 4) pc0 |= c << (8 * k);
+      else pc1 |= c << (8 * (k - 4));
+      id[k] &= rp.id_mask;
+    }
+  }
   // hand the last key (and its "short" flag) of every thread to its right neighbour
   s_lastkey[tid] = key[IPT - 1];
   if (ROUND0) s_lastshort[tid] = (j0 + IPT - 1 < m && id[IPT - 1] >= rp.short_thresh) ? 1u : 0u;
@@ -812,7 +841,7 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
     if (ROUND0) prevshort = s_lastshort[tid - 1];
   } else if (tile_base > 0) {
     prevkey = keys[tile_base - 1];
-    if (ROUND0) prevshort = (idx[tile_base - 1] >= rp.short_thresh) ? 1u : 0u;
+    if (ROUND0) prevshort = ((idx[tile_base - 1] & rp.id_mask) >= rp.short_thresh) ? 1u : 0u;
   } else {
     prevkey = 0;
     has_prev = false;
@@ -960,7 +989,9 @@ __global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, c
       }
       const bool in_win = (id[k] >= rp.win_lo) && (id[k] < rp.win_hi);
       if (single && in_win && id[k] > 0) {  // emit L[nr] = T[id-1]  (suffix 0 owns the hole at pidx)
-        const uint8_t ch = ep.text[id[k] - 1];
+        uint8_t ch;
+        if (ROUND0 && rp.packed) ch = s_dec[((k < 4 ? pc0 >> (8 * k) : pc1 >> (8 * (k - 4)))) & 0xFFu];
+        else ch = ep.text[id[k] - 1];
         if (ep.block_mode && nr == ep.N - 1) *ep.lastch = 0x100u | ch;
         else ep.out[nr] = ch;
       }
