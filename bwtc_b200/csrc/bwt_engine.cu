@@ -589,7 +589,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       CK(ctx, cudaMemsetAsync(ctx->d_ctrl(), 0, CTR_WORDS * 4, st));
       k_seg_round<<<div_up(m, SEG_T), 256, 0, st>>>(pool[list_nr], pool[list_id], m, ctx->d_rank, N, h32, ep, pool[out_nr],
                                                     pool[out_id], pool[up_a], pool[up_b], ctx->d_ctrl());
-      k_apply_ranks<<<ctx->sm_count * 4, 256, 0, st>>>(pool[up_a], pool[up_b], ctx->d_ctrl(), ctx->d_rank);
+      k_apply_ranks<<<ctx->sm_count * 8, 256, 0, st>>>(pool[up_a], pool[up_b], ctx->d_ctrl(), ctx->d_rank);
       CK(ctx, cudaGetLastError());
       S.kernel_launches += 2;
       S.algorithmic_bytes += (uint64_t)m * 32;

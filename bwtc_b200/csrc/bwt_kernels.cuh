@@ -761,7 +761,7 @@ struct EmitParams {
 };
 
 template <typename KeyT, bool ROUND0>
-__global__ void __launch_bounds__(256) k_rerank(const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx,
+__global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx,
                                                 uint32_t* __restrict__ rank, RerankParams rp,
                                                 unsigned long long* __restrict__ tstate,
                                                 uint32_t* __restrict__ ctrl, EmitParams ep, StageParams sp) {
@@ -1093,15 +1093,21 @@ __global__ void __launch_bounds__(256) k_scatter_bucket(const uint32_t* __restri
 // staged chunk to out[excl[t] ..) — the concatenation keeps the sorted order, so groups stay contiguous.
 __global__ void __launch_bounds__(1024) k_scan_tile_counts(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ excl,
                                                            uint32_t ntiles) {
+  constexpr int PER = 16;  // counts per thread and sweep: 16 independent loads in flight, one CTA scan per 16384 tiles
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_carry = 0;
   __syncthreads();
-  for (uint32_t base = 0; base < ntiles; base += 1024) {
-    const uint32_t i = base + tid;
-    const uint32_t v = (i < ntiles) ? cnt[i] : 0u;
-    uint32_t inc = v;
+  for (uint32_t base = 0; base < ntiles; base += 1024 * PER) {
+    const uint32_t i0 = base + (uint32_t)tid * PER;
+    uint32_t v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) v[k] = (i0 + k < ntiles) ? cnt[i0 + k] : 0u;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) sum += v[k];
+    uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
@@ -1110,9 +1116,15 @@ __global__ void __launch_bounds__(1024) k_scan_tile_counts(const uint32_t* __res
     if (lane == 31) s_w[warp] = inc;
     __syncthreads();
     uint32_t woff = 0, total = 0;
+#pragma unroll
     for (int w = 0; w < 32; ++w) { const uint32_t t = s_w[w]; if (w < warp) woff += t; total += t; }
     const uint32_t carry = s_carry;
-    if (i < ntiles) excl[i] = carry + woff + inc - v;
+    uint32_t run = carry + woff + inc - sum;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      if (i0 + k < ntiles) excl[i0 + k] = run;
+      run += v[k];
+    }
     __syncthreads();
     if (tid == 0) s_carry = carry + total;
     __syncthreads();
@@ -1267,7 +1279,9 @@ __global__ void __launch_bounds__(256) k_seg_round(const uint32_t* __restrict__ 
     uint32_t ireg[IPT], npos[IPT];
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
-      const uint32_t j = tid * IPT + k;
+      // striped (record tid + 256k): the members of a long group are spread over many threads and the lanes of a
+      // warp walk the same group together (broadcast reads), instead of one thread owning 8 members of it
+      const uint32_t j = (uint32_t)tid + 256u * k;
       npos[k] = 0xFFFFFFFFu;
       if (j < L) {
         kreg[k] = s_key[j];
@@ -1411,7 +1425,14 @@ __global__ void __launch_bounds__(256) k_seg_round(const uint32_t* __restrict__ 
 __global__ void __launch_bounds__(256) k_apply_ranks(const uint32_t* __restrict__ upd_id, const uint32_t* __restrict__ upd_nr,
                                                      const uint32_t* __restrict__ ctrl, uint32_t* __restrict__ rank) {
   const uint32_t n = ctrl[CTR_UPD];
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) rank[upd_id[j]] = upd_nr[j];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; j + 3 * stride < n; j += 4 * stride) {  // four independent (id, rank) loads and stores in flight per thread
+    const uint32_t i0 = upd_id[j], i1 = upd_id[j + stride], i2 = upd_id[j + 2 * stride], i3 = upd_id[j + 3 * stride];
+    const uint32_t r0 = upd_nr[j], r1 = upd_nr[j + stride], r2 = upd_nr[j + 2 * stride], r3 = upd_nr[j + 3 * stride];
+    rank[i0] = r0; rank[i1] = r1; rank[i2] = r2; rank[i3] = r3;
+  }
+  for (; j < n; j += stride) rank[upd_id[j]] = upd_nr[j];
 }
 
 // =====================================================================================================
