@@ -302,8 +302,8 @@ def main_gpu(args):
                     "bytes_per_launch": sort_bytes / max(sort_launches, 1),
                     "avg_launch_ms": sort_ms / max(sort_launches, 1), "launches_timed": sort_launches,
                     "share_of_block_gpu_time": all_sort_ms / gpu_ms,
-                    "launch_shape": "round-0 passes only: 33 554 433 records of (u64 key, u32 id) per launch; the "
-                                    "7 passes of the small doubling round are launch-latency-bound and excluded",
+                    "launch_shape": "the 8 round-0 digit passes: 33 554 433 records of (u64 key, u32 id) per launch "
+                                    "(later rounds of this workload are sort-free: k_seg_round / k_small_rounds)",
                     "whole_block": {"algorithmic_bytes_per_input_byte": alg_bytes / (4.0 * n) if nb >= 4 else None,
                                     "achieved_gbs": alg_bytes / 1e9 / (gpu_ms / 1e3),
                                     "frac_of_peak": alg_bytes / 1e9 / (gpu_ms / 1e3) / peak,
