@@ -194,6 +194,8 @@ def main_gpu(args):
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from bwtc_b200 import sharding
+    bound_cpus = sharding.bind_host_to_gpu(local_rank) if world > 1 else 0  # NUMA-local staging buffers and workers
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -207,7 +209,6 @@ def main_gpu(args):
     host_in = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(nb)]
     host_out = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(nb)]
     # block i of the global stream -> rank i mod G (bwtc_b200/sharding.py); seeds follow the GLOBAL block index
-    from bwtc_b200 import sharding
     mine = sharding.blocks_for_rank(nb * world, rank, world)
     assert len(mine) == nb
     with ThreadPoolExecutor(max_workers=min(nb, os.cpu_count() or 1)) as ex:
@@ -323,7 +324,8 @@ def main_gpu(args):
                 "config": {"workload": WORKLOAD, "pipeline_depth": args.depth,
                            "l2": "every step streams 512 MiB of fresh blocks per GPU through ~1 GiB of scratch per "
                                  "in-flight block, far larger than the 126 MB L2 (no flush needed)",
-                           "parallelism": "independent blocks sharded by rank, no collective on the data path"},
+                           "parallelism": "independent blocks sharded by rank, no collective on the data path",
+                           "host": "rank 0 bound to %s host cores (NVML affinity of its GPU)" % (bound_cpus if bound_cpus else "all")},
                 "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": nb * n,
                         "d2h_bytes_per_step": nb * (n + 4 * STARTS + 256 * 4)},
                 "gpu_launches": int(ltot.item()),

@@ -61,3 +61,37 @@ def run_sharded(blocks: Dict[int, np.ndarray], total_blocks: int, rank: int, wor
         if m["owner"] != owner_of(m["index"], world):
             raise RuntimeError("block %d transformed by the wrong rank" % m["index"])
     return merged
+
+
+def bind_host_to_gpu(device: int):
+    """Pin this process (and the worker threads it creates later) to the host cores NVML reports as local to
+    `device` — pinned staging buffers are then first-touched on the GPU's NUMA node and H2D/D2H copies do not
+    cross the socket interconnect.  One process per GPU (torchrun) calls this once, before allocating pinned
+    memory.  Returns the number of cores bound to, or 0 if nothing was changed (single socket, NVML missing,
+    BWTC_NUMA_BIND=0).  Host-side plumbing only: no effect on results."""
+    import os
+
+    if os.environ.get("BWTC_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return 0
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = None
+        try:
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(device).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus or len(cpus) >= len(os.sched_getaffinity(0)):
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
