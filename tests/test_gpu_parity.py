@@ -174,6 +174,42 @@ def test_pipeline_equals_single_context(oracle):
     pipe.close()
 
 
+ENGINE_KNOBS = [
+    {},                                                              # defaults
+    {"BWTC_RERANK_WINDOW_MB": "1"},                                  # >= 3 id windows at 1-2 MiB: bucketed rank scatter
+    {"BWTC_RERANK_WINDOW_MB": "1", "BWTC_BUCKET_MIN_WINDOWS": "0"},  # one k_rerank launch per id window
+    {"BWTC_RERANK_WINDOW_MB": "4", "BWTC_BUCKET_MIN_WINDOWS": "2"},  # bucketed scatter with exactly two buckets
+    {"BWTC_PACK_PRED": "0"},                                         # BWT characters gathered from the text
+    {"BWTC_SEG": "0"},                                               # global radix rounds only (no segmented rounds)
+    {"BWTC_SEG": "0", "BWTC_RERANK_WINDOW_MB": "1"},                 # bucketed scatter in doubling rounds too
+]
+
+
+@pytest.mark.parametrize("knobs", ENGINE_KNOBS, ids=lambda k: ",".join(f"{a[5:]}={b}" for a, b in k.items()) or "default")
+def test_every_engine_path_is_bit_exact(oracle, monkeypatch, knobs):
+    """The engine picks between code paths by block size (L2 windows of the rank scatter, packed predecessor
+    characters, segmented vs global rounds).  The tuning knobs are read when a context is created, so every path can
+    be forced at sizes the oracle handles: all of them must produce the oracle's bytes."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    n = (2 << 20) + 4097
+    ctx = bw.CudaContext(n)
+    rng = np.random.default_rng(77)
+    cases = [("markov", n), ("dna", n), ("repetitive", 1 << 20), ("random", n - 4099)]
+    try:
+        for kind, sz in cases:
+            x = bw.generate(kind, sz, seed=41)
+            if kind == "random":
+                x[rng.integers(0, sz, 1000)] = 0  # zeros inside the block: the sentinel shares a code with data
+            want = oracle.block(x, 8)
+            got = _gpu_block(ctx, x, 8)
+            assert (got[0] == want[0]).all(), (kind, knobs)
+            assert (got[1] == want[1]).all(), (kind, knobs)
+            assert (got[2] == want[2]).all(), (kind, knobs)
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("kind,mib", [("markov", 32), ("dna", 64), ("repetitive", 16), ("random", 64)])
 def test_full_size_properties(reference, kind, mib):
     """BASELINE.json block sizes: size-independent properties instead of the (slow) oracle —
