@@ -98,6 +98,8 @@ C_ABI = [
     ("bwtc_cuda_divbwt", ctypes.c_int64, [_vp, _vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32]),
     ("bwtc_cuda_bwt_block", ctypes.c_int64, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _vp]),
     ("bwtc_cuda_bwt_block_device", ctypes.c_int64, [_vp, _vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _vp]),
+    ("bwtc_cuda_bwt_blocks", ctypes.c_int,
+     [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _vp, _vp, _vp]),
     ("bwtc_cuda_num_starting_points", ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32]),
     ("bwtc_cuda_pipeline_create", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_uint32]),
     ("bwtc_cuda_pipeline_destroy", None, [_vp]),
@@ -203,6 +205,19 @@ class CudaContext:
         assert block.dtype == np.uint8 and LFpowers.dtype == np.uint32
         return self._check(self._lib.bwtc_cuda_bwt_block(self._h, block.ctypes.data, block.size,
                                                           LFpowers.ctypes.data, LFpowers.size, _ptr(freqs)))
+
+    def bwt_blocks(self, blocks, starts: int, want_freqs: bool = True):
+        """bwtc_cuda_bwt_blocks: transform the given uint8 arrays IN PLACE (equal-sized runs are batched into one
+        device-side sort).  Returns (LFpowers[count, 256], nLF[count], freqs[count, 256] or None)."""
+        count = len(blocks)
+        ptrs = (ctypes.c_void_p * count)(*[b.ctypes.data for b in blocks])
+        sizes = np.array([b.size for b in blocks], dtype=np.uint32)
+        LF = np.zeros((count, 256), dtype=np.uint32)
+        nLF = np.zeros(count, dtype=np.uint32)
+        fr = np.zeros((count, 256), dtype=np.uint32) if want_freqs else None
+        self._check(self._lib.bwtc_cuda_bwt_blocks(self._h, ptrs, sizes.ctypes.data, count, starts, 0, LF.ctypes.data,
+                                                   nLF.ctypes.data, _ptr(fr)))
+        return LF, nLF, fr
 
     def bwt_block_device(self, d_in: int, d_out: int, n: int, LFpowers: np.ndarray,
                          freqs: Optional[np.ndarray]) -> int:

@@ -48,6 +48,9 @@ inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) /
 
 }  // namespace
 
+constexpr uint32_t MAX_BATCH = BWTC_CUDA_MAX_BATCH;  // blocks sorted as one text (6 key bits for the block number)
+constexpr uint32_t LF_PARK = MAX_BATCH * 256, LF_WATCH = LF_PARK + MAX_BATCH, LF_WORDS = LF_WATCH + 8;
+
 struct bwtc_cuda_ctx {
   int device = 0;
   int sm_count = 148;
@@ -62,10 +65,15 @@ struct bwtc_cuda_ctx {
   uint32_t* d_idx[2] = {nullptr, nullptr};
   uint32_t* d_zero = nullptr;  // [ctrl CTR_WORDS][hist HIST_WORDS][tstate 2*max_aux_tiles] zeroed per round
   uint32_t* d_status = nullptr;  // [MAX_PASSES][max_rs_tiles][256]
-  uint32_t* d_LF = nullptr;
+  uint32_t* d_LF = nullptr;       // [LF_PARK) LFpowers (one row of 256 per block of a batch), [LF_PARK + k] parked hole byte
+                                  // of block k, [LF_WATCH] watchdog word of k_small_rounds
+  uint32_t* d_bhist = nullptr;    // [MAX_BATCH][256] per-block byte histograms of a batch
+  const uint8_t** d_bptr = nullptr;  // [MAX_BATCH] device pointers to the blocks of a batch
+  uint8_t* h_batch = nullptr;     // pinned: [MAX_BATCH] pointers, [MAX_BATCH][256] histograms, [MAX_BATCH][256] LFpowers
   uint32_t* d_tilecnt = nullptr;  // [2][max_aux_tiles]: per-tile live counts of k_rerank and their exclusive prefix,
                                   // then [max_aux_tiles][MAX_RERANK_WINDOWS+1] bucket offsets of the bucketed scatter
   uint32_t* d_scat = nullptr;     // u32[N]: staged ranks of the bucketed scatter (the ids go to the idle id buffer)
+  int use_batch = 1;              // small equal-sized blocks of one call are sorted as one text (BWTC_BATCH=0: never)
   int use_pack_pred = 1;          // carry code(T[id-1]) above the id through the round-0 sort when it fits
   int bucket_min_windows = 3;     // bucketed scatter from this many L2 windows on (0 = never)
   unsigned long long* d_wtab = nullptr;  // window-sample table: WS_SLOTS keys, WS_SLOTS counters, 2 doubles
@@ -116,6 +124,8 @@ void ctx_free(bwtc_cuda_ctx* c) {
   cudaFree(c->d_in); cudaFree(c->d_text); cudaFree(c->d_out); cudaFree(c->d_rank);
   cudaFree(c->d_keys[0]); cudaFree(c->d_keys[1]); cudaFree(c->d_idx[0]); cudaFree(c->d_idx[1]);
   cudaFree(c->d_zero); cudaFree(c->d_status); cudaFree(c->d_LF); cudaFree(c->d_wtab); cudaFree(c->d_tilecnt); cudaFree(c->d_scat);
+  cudaFree(c->d_bhist); cudaFree(c->d_bptr);
+  if (c->h_batch) cudaFreeHost(c->h_batch);
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -130,21 +140,24 @@ struct Round0Plan {
 };
 
 // Dense alphabet + round-0 key shape.  present[c] != 0 for every byte of the text.
+// blk_bits > 0 (batch of blocks sorted as one text): code 0 is reserved for the sentinel positions, and blk_bits key
+// bits above the characters hold the block number.
 void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* present, uint32_t N,
-                 const double* pair_stats, Round0Plan* pl) {
-  uint32_t sigma = 0;
+                 const double* pair_stats, Round0Plan* pl, uint32_t blk_bits = 0) {
+  uint32_t sigma = blk_bits ? 1u : 0u;
   double total = 0, H0 = 0;
   for (int c = 0; c < 256; ++c) {
     pl->pp.lut[c] = 0;
     if (present[c]) { pl->pp.lut[c] = (uint8_t)sigma; ++sigma; total += (double)count[c]; }
   }
+  if (sigma > 256) sigma = 256;  // 256 data bytes + reserved sentinel: handled by the caller (falls back to single blocks)
   for (int c = 0; c < 256; ++c)
     if (present[c] && count[c]) { double p = (double)count[c] / total; H0 -= p * std::log2(p); }
   const uint32_t b = sigma <= 2 ? 1 : ceil_log2_u64(sigma);
-  const uint32_t cmax64 = 64 / b, cmax32 = 32 / b;
+  const uint32_t cmax64 = (64 - blk_bits) / b, cmax32 = blk_bits >= 32 - b ? 0u : (32 - blk_bits) / b;
   uint32_t chars, keybytes;
   if (ctx->force_chars || ctx->force_keybytes) {
-    keybytes = ctx->force_keybytes == 4 ? 4 : 8;
+    keybytes = (ctx->force_keybytes == 4 && cmax32 >= 1) ? 4 : 8;
     const uint32_t cmax = keybytes == 4 ? cmax32 : cmax64;
     chars = ctx->force_chars ? ctx->force_chars : cmax;
     if (chars > cmax) chars = cmax;
@@ -174,26 +187,28 @@ void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* pr
       double best = 1e300;
       chars = cmax64;
       for (uint32_t c = 1; c <= cmax64; ++c) {
-        const double p0 = std::ceil((double)c * b / 8.0) * ((uint64_t)c * b > 32 ? 1.1 : 1.0);
+        const double p0 = std::ceil(((double)c * b + blk_bits) / 8.0) * ((uint64_t)c * b + blk_bits > 32 ? 1.1 : 1.0);
         const double L = 1.0 - std::exp(-(double)N * std::exp2(-H0 * (double)c));
         const double cost = p0 + L * (npd + 2.0);
         if (cost < best - 1e-9) { best = cost; chars = c; }
       }
       // use every bit of the last digit pass that is executed anyway
-      const uint32_t np = div_up((uint64_t)chars * b, 8);
-      const uint32_t cfull = (8 * np) / b;
-      const uint32_t cap = ((uint64_t)chars * b <= 32) ? cmax32 : cmax64;
+      const uint32_t np = div_up((uint64_t)chars * b + blk_bits, 8);
+      const uint32_t cfull = (8 * np - blk_bits) / b;
+      const uint32_t cap = ((uint64_t)chars * b + blk_bits <= 32) ? cmax32 : cmax64;
       chars = cfull < cap ? cfull : cap;
-      keybytes = ((uint64_t)chars * b <= 32) ? 4 : 8;
+      keybytes = ((uint64_t)chars * b + blk_bits <= 32) ? 4 : 8;
     }
   }
   pl->sigma = sigma;
   pl->bits = b;
   pl->chars = chars;
   pl->keybytes = keybytes;
-  pl->npass = div_up((uint64_t)chars * b, 8);
+  pl->npass = div_up((uint64_t)chars * b + blk_bits, 8);
   pl->pp.bits = b;
   pl->pp.chars = chars;
+  pl->pp.nblocks = 1;
+  pl->pp.stride = 0;
 }
 
 // Number of id windows the rank scatter of a round is split into (k_rerank RerankParams::win_lo/hi).
@@ -234,7 +249,8 @@ struct PassTimer {
 // between buffer 0 and 1.  Records start in buffer `cur` (0); returns the buffer holding the result.
 template <typename KeyT, int IPT>
 int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota, uint32_t iota_top, int* cur_io,
-             PassTimer* pt, uint32_t* passes_done, uint32_t pack_bits = 0, uint32_t topshift = 0) {
+             PassTimer* pt, uint32_t* passes_done, uint32_t pack_bits = 0, uint32_t topshift = 0,
+             uint32_t pred_mask = 0xFFFFFFFFu) {
   constexpr uint32_t TILE = RS_BLOCK * IPT;
   const uint32_t tiles = div_up(m, TILE);
   const size_t smem = RadixPassSmem<KeyT, RS_BLOCK, IPT>::bytes;
@@ -250,11 +266,11 @@ int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota
     if (iota)
       k_radix_pass<KeyT, RS_BLOCK, IPT, true><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-          CTR_PASS0 + p, iota_top, pack_bits, topshift);
+          CTR_PASS0 + p, iota_top, pack_bits, topshift, pred_mask);
     else
       k_radix_pass<KeyT, RS_BLOCK, IPT, false><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, ctx->d_idx[cur], kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-          CTR_PASS0 + p, iota_top, 0u, 0u);
+          CTR_PASS0 + p, iota_top, 0u, 0u, 0u);
     CK(ctx, cudaGetLastError());
     if (pt->end()) return BWTC_CUDA_ECUDA;
     ctx->stats.kernel_launches++;
@@ -325,14 +341,36 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
   return 0;
 }
 
+// A batch of small blocks transformed as ONE suffix-sorting problem: text = T'_0 T'_1 ... with
+// T'_k = reverse(X_k) . 0x00 at offset k * (n0 + 1).  All blocks have n0 bytes, the last one n_last <= n0.
+struct BatchSpec {
+  uint32_t nblocks, n0, n_last;
+  const void* const* in;  // per block: host pointers, or device pointers when on_device
+  void* const* out;
+  bool on_device;
+  uint32_t* LF;           // [nblocks][256]
+  uint32_t nLF, nLF_last; // LFpowers per full block / for the last block
+  uint32_t* freqs;        // [nblocks][256] incremented, or nullptr
+};
+constexpr int64_t BATCH_NEEDS_SINGLE = -1000;  // all 256 byte values present: no code left for the reserved sentinel
+
 // The engine proper.  block_mode: in = X (n block bytes), result n bytes.  raw: in = T (n bytes), result n bytes.
 // in_dev / out_dev: device pointers supplied by the caller (or nullptr -> staged through the context).
+// bs != nullptr: batch of blocks (block contract); h_in/h_out/in_dev/out_dev/LF/nLF/freqs come from *bs.
 int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, uint8_t* h_out, const uint8_t* in_dev,
-                      uint8_t* out_dev, uint32_t n, uint32_t* LF, uint32_t nLF, uint32_t* freqs) {
+                      uint8_t* out_dev, uint32_t n, uint32_t* LF, uint32_t nLF, uint32_t* freqs,
+                      const BatchSpec* bs = nullptr) {
   ctx->err[0] = 0;
   if (cudaSetDevice(ctx->device) != cudaSuccess) {
     set_err(ctx->err, "cudaSetDevice(%d) failed", ctx->device);
     return BWTC_CUDA_ECUDA;
+  }
+  const uint32_t bstride = bs ? bs->n0 + 1u : 0u;
+  if (bs) {
+    n = (bs->nblocks - 1u) * bstride + bs->n_last;  // N - 1
+    nLF = bs->nLF;
+    LF = bs->LF;
+    freqs = bs->freqs;
   }
   const uint32_t N = block_mode ? n + 1 : n;
   if (n > ctx->cap) {
@@ -351,18 +389,41 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
 
   // ---- input
   const uint8_t* d_src = in_dev;
-  if (!in_dev) {
+  const void** h_bptr = reinterpret_cast<const void**>(ctx->h_batch);
+  uint32_t* h_bhist = reinterpret_cast<uint32_t*>(ctx->h_batch + MAX_BATCH * sizeof(void*));
+  uint32_t* h_bLF = h_bhist + MAX_BATCH * 256;
+  if (bs) {
+    for (uint32_t k = 0; k < bs->nblocks; ++k) {
+      const uint32_t nk = (k + 1 == bs->nblocks) ? bs->n_last : bs->n0;
+      if (bs->on_device) {
+        h_bptr[k] = bs->in[k];
+      } else {
+        CK(ctx, cudaMemcpyAsync(ctx->d_in + (size_t)k * bs->n0, bs->in[k], nk, cudaMemcpyHostToDevice, st));
+        h_bptr[k] = ctx->d_in + (size_t)k * bs->n0;
+      }
+    }
+    CK(ctx, cudaMemcpyAsync(ctx->d_bptr, h_bptr, bs->nblocks * sizeof(void*), cudaMemcpyHostToDevice, st));
+    d_src = ctx->d_text;  // the policy sample reads the (reversed) concatenation
+  } else if (!in_dev) {
     CK(ctx, cudaMemcpyAsync(ctx->d_in, h_in, n, cudaMemcpyHostToDevice, st));
     d_src = ctx->d_in;
   }
-  uint8_t* d_dst = out_dev ? out_dev : ctx->d_out;
+  uint8_t* d_dst = (out_dev && !bs) ? out_dev : ctx->d_out;
   CK(ctx, cudaEventRecord(ctx->ev_begin, st));
 
   // ---- byte histogram (+ reversed, sentinel-terminated text in block mode)
   CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)(CTR_WORDS + HIST_WORDS) * 4, st));
   const uint8_t* d_text;
   const int pgrid = ctx->sm_count * 8;
-  if (block_mode) {
+  if (bs) {
+    const uint32_t padded_words = div_up((uint64_t)N + TEXT_PAD, 4);
+    CK(ctx, cudaMemsetAsync(ctx->d_bhist, 0, (size_t)bs->nblocks * 256 * 4, st));
+    const dim3 grid(std::max<uint32_t>(1u, div_up((uint32_t)pgrid, bs->nblocks)), bs->nblocks);
+    k_prep_batch<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t* const*>(ctx->d_bptr), bs->n0, bs->n_last, bs->nblocks,
+                                       ctx->d_text, N, padded_words, ctx->d_bhist);
+    d_text = ctx->d_text;
+    S.algorithmic_bytes += 2ull * n + N;
+  } else if (block_mode) {
     const uint32_t padded_words = div_up((uint64_t)N + TEXT_PAD, 4);
     k_prep_block<<<pgrid, 256, 0, st>>>(d_src, n, ctx->d_text, padded_words, ctx->d_hist());
     d_text = ctx->d_text;
@@ -391,22 +452,36 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     }
     CK(ctx, cudaMemcpyAsync(ctx->h_LF() + 256, d_pairs, 16, cudaMemcpyDeviceToHost, st));
   }
-  CK(ctx, cudaMemcpyAsync(ctx->h_hist(), ctx->d_hist(), 256 * 4, cudaMemcpyDeviceToHost, st));
+  if (bs) CK(ctx, cudaMemcpyAsync(h_bhist, ctx->d_bhist, (size_t)bs->nblocks * 256 * 4, cudaMemcpyDeviceToHost, st));
+  else CK(ctx, cudaMemcpyAsync(ctx->h_hist(), ctx->d_hist(), 256 * 4, cudaMemcpyDeviceToHost, st));
   CK(ctx, cudaStreamSynchronize(st));
 
   uint64_t count[256];
   bool present[256];
+  uint32_t npresent = 0;
   for (int c = 0; c < 256; ++c) {
-    count[c] = ctx->h_hist()[c];
+    count[c] = 0;
+    if (bs) for (uint32_t k = 0; k < bs->nblocks; ++k) count[c] += h_bhist[k * 256 + c];
+    else count[c] = ctx->h_hist()[c];
     present[c] = count[c] != 0;
-    if (freqs) freqs[c] += ctx->h_hist()[c];
+    npresent += present[c] ? 1u : 0u;
+  }
+  if (bs && npresent >= 256) return BATCH_NEEDS_SINGLE;  // nothing has been written to the caller's arrays yet
+  if (freqs) {
+    for (int c = 0; c < 256; ++c) {
+      if (bs) for (uint32_t k = 0; k < bs->nblocks; ++k) freqs[k * 256 + c] += h_bhist[k * 256 + c];
+      else freqs[c] += ctx->h_hist()[c];
+    }
   }
   // Block contract: the appended 0x00 only enters the alphabet if the block itself contains 0x00.  Otherwise
   // it is a true sentinel: it gets code 0 like the padding past the end, and the "window ran past the end"
   // rule of the round-0 re-rank starts one position earlier — a 4-letter alphabet then packs
-  // into 2 bits per character instead of 3.
+  // into 2 bits per character instead of 3.  A batch reserves code 0 for its sentinels instead (§3.6).
   bool sentinel_outside_alphabet = false;
-  if (block_mode) {
+  uint32_t blk_bits = 0;
+  if (bs) {
+    blk_bits = std::max<uint32_t>(1u, (uint32_t)ceil_log2_u64(bs->nblocks));
+  } else if (block_mode) {
     if (!present[0]) sentinel_outside_alphabet = true;
   } else {
     const uint8_t last = h_in[N - 1];
@@ -417,14 +492,17 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   double pair_stats[2];  // [0] colliding pairs among the sampled 8-byte windows, [1] samples
   memcpy(pair_stats, ctx->h_LF() + 256, 16);
   Round0Plan pl;
-  plan_round0(ctx, count, present, N, pair_stats, &pl);
+  plan_round0(ctx, count, present, N, pair_stats, &pl, blk_bits);
+  if (bs) { pl.pp.nblocks = bs->nblocks; pl.pp.stride = bstride; }
   EmitParams ep;
+  ep.nblocks = bs ? bs->nblocks : 1u;
+  ep.stride = bstride;
   ep.text = d_text;
   ep.out = d_dst;
-  ep.lastch = ctx->d_LF + 256;
+  ep.lastch = ctx->d_LF + LF_PARK;
   ep.N = N;
   ep.block_mode = block_mode ? 1 : 0;
-  CK(ctx, cudaMemsetAsync(ctx->d_LF + 256, 0, 8, st));  // [256] parked hole byte, [257] tail-kernel watchdog
+  CK(ctx, cudaMemsetAsync(ctx->d_LF + LF_PARK, 0, (size_t)(LF_WORDS - LF_PARK) * 4, st));  // parked hole bytes, tail-kernel watchdog
   S.sigma = pl.sigma;
   S.bits_per_char = pl.bits;
   S.chars_round0 = pl.chars;
@@ -445,7 +523,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     for (uint32_t p = 0; p < pl.npass; ++p) {
       int rep = -1;
       const bool full_p = (8 * p + 8 <= keybits);
-      if (full_p && N > 64)
+      if (full_p && N > 64 && !bs)  // (a batch counts every digit directly: block numbers sit above the characters)
         for (uint32_t r = 0; r < p; ++r)
           if (((hist_mask >> r) & 1u) && (8 * r) % pl.bits == (8 * p) % pl.bits && (8 * (p - r)) % pl.bits == 0) { rep = (int)r; break; }
       if (rep < 0) {
@@ -483,10 +561,13 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   if (id_bits < 1) id_bits = 1;
   const bool pack_pred = ctx->use_pack_pred && (id_bits + pl.bits <= 32) && (mask0 & 1u);
   const uint32_t topshift = (pl.chars - 1) * pl.bits;
+  const uint32_t pred_mask = (1u << pl.bits) - 1u;  // (a batch key carries the block number above the characters)
   if (pl.keybytes == 4)
-    rc = run_sort<uint32_t, RS_IPT32>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone, pack_pred ? id_bits : 0u, topshift);
+    rc = run_sort<uint32_t, RS_IPT32>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone, pack_pred ? id_bits : 0u, topshift,
+                                      pred_mask);
   else
-    rc = run_sort<unsigned long long, RS_IPT64>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone, pack_pred ? id_bits : 0u, topshift);
+    rc = run_sort<unsigned long long, RS_IPT64>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone, pack_pred ? id_bits : 0u,
+                                                topshift, pred_mask);
   if (rc) return rc;
   const size_t round0_events = pt.used;
   S.sort0_launches = S.sort_launches;
@@ -567,7 +648,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     if (m <= (uint32_t)SMALL_MAX) {
       // tail: one CTA finishes all remaining rounds on the device
       if (!have_lists && make_lists()) return BWTC_CUDA_ECUDA;
-      k_small_rounds<<<1, 1024, 0, st>>>(pool[list_id], m, ctx->d_rank, N, h32, ep, ctx->d_LF + 257);
+      k_small_rounds<<<1, 1024, 0, st>>>(pool[list_id], m, ctx->d_rank, N, h32, ep, ctx->d_LF + LF_WATCH);
       CK(ctx, cudaGetLastError());
       S.kernel_launches++;
       S.algorithmic_bytes += (uint64_t)m * 24;
@@ -680,21 +761,41 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
 
   // ---- final: fused BWT emission + pidx + LFpowers (+ hole fill)
   {
-    k_finish<<<1, 256, 0, st>>>(ctx->d_rank, d_text, N, d_dst, block_mode ? 1 : 0, ctx->d_LF, nLF, ctx->d_LF + 256);
+    if (bs)
+      k_finish_batch<<<bs->nblocks, 256, 0, st>>>(ctx->d_rank, N, bstride, bs->nblocks, d_dst, ctx->d_LF, bs->nLF, bs->nLF_last,
+                                                  ctx->d_LF + LF_PARK);
+    else
+      k_finish<<<1, 256, 0, st>>>(ctx->d_rank, d_text, N, d_dst, block_mode ? 1 : 0, ctx->d_LF, nLF, ctx->d_LF + LF_PARK);
     CK(ctx, cudaGetLastError());
     S.kernel_launches++;
     S.algorithmic_bytes += (uint64_t)N * 2;  // text gather + BWT byte, charged once per suffix (done inside k_rerank)
   }
   CK(ctx, cudaEventRecord(ctx->ev_end, st));
-  CK(ctx, cudaMemcpyAsync(ctx->h_LF(), ctx->d_LF, nLF * 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_LF + 257, 4, cudaMemcpyDeviceToHost, st));
-  if (!out_dev) CK(ctx, cudaMemcpyAsync(h_out, ctx->d_out, n, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_LF + LF_WATCH, 4, cudaMemcpyDeviceToHost, st));
+  if (bs) {
+    CK(ctx, cudaMemcpyAsync(h_bLF, ctx->d_LF, (size_t)bs->nblocks * 256 * 4, cudaMemcpyDeviceToHost, st));
+    for (uint32_t k = 0; k < bs->nblocks; ++k) {  // block k's BWT bytes are out[k*stride .. k*stride + n_k)
+      const uint32_t nk = (k + 1 == bs->nblocks) ? bs->n_last : bs->n0;
+      CK(ctx, cudaMemcpyAsync(bs->out[k], ctx->d_out + (size_t)k * bstride, nk,
+                              bs->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    }
+  } else {
+    CK(ctx, cudaMemcpyAsync(ctx->h_LF(), ctx->d_LF, nLF * 4, cudaMemcpyDeviceToHost, st));
+    if (!out_dev) CK(ctx, cudaMemcpyAsync(h_out, ctx->d_out, n, cudaMemcpyDeviceToHost, st));
+  }
   CK(ctx, cudaStreamSynchronize(st));
   if (ctx->h_ctrl()[0]) {
     set_err(ctx->err, "tail refinement kernel did not converge (code %u)", ctx->h_ctrl()[0]);
     return BWTC_CUDA_EINTERNAL;
   }
-  for (uint32_t j = 0; j < nLF; ++j) LF[j] = ctx->h_LF()[j];
+  if (bs) {
+    for (uint32_t k = 0; k < bs->nblocks; ++k) {
+      const uint32_t nl = (k + 1 == bs->nblocks) ? bs->nLF_last : bs->nLF;
+      for (uint32_t j = 0; j < nl; ++j) LF[k * 256 + j] = h_bLF[k * 256 + j];
+    }
+  } else {
+    for (uint32_t j = 0; j < nLF; ++j) LF[j] = ctx->h_LF()[j];
+  }
   float ms = 0;
   CK(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
   S.gpu_ms = ms;
@@ -710,6 +811,60 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     S.sort0_ms = tot0;
   }
   return (int64_t)LF[0];
+}
+
+// count blocks (block contract) through one context: as ONE batch when they qualify — 2..MAX_BATCH blocks, all of
+// sizes[0] bytes except the last which may be shorter, together within the context's capacity, and at least one byte
+// value unused (the batch reserves a code for its sentinels) — otherwise one after the other.  Results are
+// identical either way.  LF = [count][256], nLF = [count], freqs = [count][256] or nullptr.
+bool batchable(const bwtc_cuda_ctx* ctx, const uint32_t* sizes, uint32_t count) {
+  if (!ctx->use_batch || count < 2 || count > MAX_BATCH) return false;
+  uint64_t total = 0;
+  for (uint32_t k = 0; k < count; ++k) {
+    if (sizes[k] == 0) return false;
+    if (k + 1 < count ? sizes[k] != sizes[0] : sizes[k] > sizes[0]) return false;
+    total += (uint64_t)sizes[k] + 1;
+  }
+  return total <= (uint64_t)ctx->cap + 1 && total <= (uint64_t)BWTC_CUDA_MAX_BLOCK;
+}
+
+int transform_batch(bwtc_cuda_ctx* ctx, const void* const* in, void* const* out, const uint32_t* sizes, uint32_t count,
+                    uint32_t starts, bool on_device, uint32_t* LF, uint32_t* nLF, uint32_t* freqs, bwtc_cuda_stats* stats) {
+  for (uint32_t k = 0; k < count; ++k) {
+    if (!in[k] || !out[k] || sizes[k] == 0) { set_err(ctx->err, "null or empty block %u", k); return BWTC_CUDA_EARG; }
+    nLF[k] = bwtc_cuda_num_starting_points(sizes[k], starts);
+  }
+  if (batchable(ctx, sizes, count)) {
+    BatchSpec bs;
+    bs.nblocks = count;
+    bs.n0 = sizes[0];
+    bs.n_last = sizes[count - 1];
+    bs.in = in;
+    bs.out = out;
+    bs.on_device = on_device;
+    bs.LF = LF;
+    bs.nLF = nLF[0];
+    bs.nLF_last = nLF[count - 1];
+    bs.freqs = freqs;
+    const int64_t rc = run_transform(ctx, true, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, &bs);
+    if (rc != BATCH_NEEDS_SINGLE) {
+      if (stats) for (uint32_t k = 0; k < count; ++k) stats[k] = ctx->stats;
+      return rc < 0 ? (int)rc : 0;
+    }
+  }
+  for (uint32_t k = 0; k < count; ++k) {
+    uint32_t* fr = freqs ? freqs + (size_t)k * 256 : nullptr;
+    int64_t rc;
+    if (on_device)
+      rc = run_transform(ctx, true, nullptr, nullptr, static_cast<const uint8_t*>(in[k]), static_cast<uint8_t*>(out[k]), sizes[k],
+                         LF + (size_t)k * 256, nLF[k], fr);
+    else
+      rc = run_transform(ctx, true, static_cast<const uint8_t*>(in[k]), static_cast<uint8_t*>(out[k]), nullptr, nullptr, sizes[k],
+                         LF + (size_t)k * 256, nLF[k], fr);
+    if (stats) stats[k] = ctx->stats;
+    if (rc < 0) return (int)rc;
+  }
+  return 0;
 }
 
 }  // namespace
@@ -751,6 +906,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   c->device = device;
   c->cap = max_block_bytes;
   if (const char* e = getenv("BWTC_SEG")) c->use_seg = atoi(e);
+  if (const char* e = getenv("BWTC_BATCH")) c->use_batch = atoi(e);
   if (const char* e = getenv("BWTC_PACK_PRED")) c->use_pack_pred = atoi(e);
   if (const char* e = getenv("BWTC_BUCKET_MIN_WINDOWS")) c->bucket_min_windows = atoi(e);
   if (const char* e = getenv("BWTC_RERANK_WINDOW_MB")) { long v = atol(e); if (v > 0) c->rerank_window_bytes = (uint64_t)v << 20; }
@@ -786,13 +942,16 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_idx[1], N * 4);
   ALLOC(c->d_zero, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)MAX_RERANK_WINDOWS * c->max_aux_tiles * 8 + 64);
   ALLOC(c->d_status, (size_t)MAX_PASSES * c->max_rs_tiles * 1024u);
-  ALLOC(c->d_LF, (256 + 8) * 4);
+  ALLOC(c->d_LF, (size_t)LF_WORDS * 4);
+  ALLOC(c->d_bhist, (size_t)MAX_BATCH * 256 * 4);
+  ALLOC(c->d_bptr, (size_t)MAX_BATCH * sizeof(void*));
   ALLOC(c->d_wtab, (size_t)WS_SLOTS * 12 + 64);
   ALLOC(c->d_tilecnt, (size_t)c->max_aux_tiles * (2 + MAX_RERANK_WINDOWS + 1) * 4 + 64);
   ALLOC(c->d_scat, (size_t)N * 4 + 64);
 #undef ALLOC
   if (!rc) {
     e = cudaMallocHost((void**)&c->h_small, (size_t)(CTR_WORDS + HIST_WORDS + 256 + 8) * 4);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_batch, (size_t)MAX_BATCH * (sizeof(void*) + 2 * 256 * 4));
     if (e != cudaSuccess) { set_err(g_err, "cudaMallocHost: %s", cudaGetErrorString(e)); rc = BWTC_CUDA_EALLOC; }
   }
   if (!rc && (cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess)) {
@@ -907,6 +1066,22 @@ int64_t bwtc_cuda_bwt_block(bwtc_cuda_ctx* ctx, uint8_t* block, uint32_t n, uint
   return run_transform(ctx, true, block, block, nullptr, nullptr, n, LFpowers, nLFpowers, freqs);
 }
 
+int bwtc_cuda_bwt_blocks(bwtc_cuda_ctx* ctx, void* const* blocks, const uint32_t* sizes, uint32_t count, uint32_t starts,
+                         int on_device, uint32_t* LFpowers, uint32_t* nLFpowers, uint32_t* freqs) {
+  if (!ctx) { set_err(g_err, "null context"); return BWTC_CUDA_EARG; }
+  if (!blocks || !sizes || !LFpowers || !nLFpowers || count == 0) { set_err(ctx->err, "bad arguments"); return BWTC_CUDA_EARG; }
+  for (uint32_t k0 = 0; k0 < count;) {  // runs of at most MAX_BATCH blocks
+    uint32_t k1 = std::min<uint32_t>(count, k0 + MAX_BATCH);
+    while (k1 > k0 + 1 && !batchable(ctx, sizes + k0, k1 - k0)) --k1;
+    const int rc = transform_batch(ctx, const_cast<const void* const*>(blocks + k0), blocks + k0, sizes + k0, k1 - k0, starts,
+                                   on_device != 0, LFpowers + (size_t)k0 * 256, nLFpowers + k0,
+                                   freqs ? freqs + (size_t)k0 * 256 : nullptr, nullptr);
+    if (rc < 0) return rc;
+    k0 = k1;
+  }
+  return 0;
+}
+
 int64_t bwtc_cuda_bwt_block_device(bwtc_cuda_ctx* ctx, const void* d_in, void* d_out, uint32_t n, uint32_t* LFpowers,
                                    uint32_t nLFpowers, uint32_t* freqs) {
   if (!ctx) { set_err(g_err, "null context"); return BWTC_CUDA_EARG; }
@@ -933,6 +1108,8 @@ struct bwtc_cuda_pipeline {
   cudaStream_t tstream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ev_done;
+  uint32_t batch_max_block = 0;  // blocks up to this size are batched ...
+  uint32_t batch_blocks = 1;     // ... this many at most per batch
   char err[512];
 };
 
@@ -956,9 +1133,24 @@ int bwtc_cuda_pipeline_create(bwtc_cuda_pipeline** out, int device, int depth, u
   if (!p) return BWTC_CUDA_EALLOC;
   p->device = device;
   p->err[0] = 0;
+  // Small blocks: give every context room for a batch of them (~32 MiB of text, at most MAX_BATCH blocks), so a
+  // worker sorts e.g. 32 x 1 MiB blocks as one problem instead of 32 launch-latency-bound ones.
+  uint64_t cap = max_block_bytes;
+  {
+    uint64_t target = 32ull << 20;
+    if (const char* e = getenv("BWTC_BATCH_MIB")) { const long v = atol(e); target = v > 0 ? (uint64_t)v << 20 : 0; }
+    const char* eb = getenv("BWTC_BATCH");
+    if ((!eb || atoi(eb) != 0) && max_block_bytes > 0 && (uint64_t)max_block_bytes * 2 <= target) {
+      uint64_t nb = target / max_block_bytes;
+      if (nb > MAX_BATCH) nb = MAX_BATCH;
+      p->batch_blocks = (uint32_t)nb;
+      p->batch_max_block = max_block_bytes;
+      cap = (uint64_t)max_block_bytes * nb + nb;
+    }
+  }
   for (int i = 0; i < depth; ++i) {
     bwtc_cuda_ctx* c = nullptr;
-    int rc = bwtc_cuda_ctx_create(&c, device, max_block_bytes);
+    int rc = bwtc_cuda_ctx_create(&c, device, (uint32_t)cap);
     if (rc) { bwtc_cuda_pipeline_destroy(p); return rc; }
     p->ctxs.push_back(c);
   }
@@ -996,29 +1188,34 @@ int bwtc_cuda_pipeline_run(bwtc_cuda_pipeline* p, const uint8_t* const* in, uint
                            uint32_t* freqs, bwtc_cuda_stats* stats) {
   if (!p || !in || !out || !sizes || !LFpowers || !nLF) { if (p) set_err(p->err, "bad arguments"); return BWTC_CUDA_EARG; }
   p->err[0] = 0;
+  // Consecutive small blocks of equal size are grouped and handed to a worker as one batch (one device-side
+  // sorting problem, see transform_batch); everything else is one block per claim.
+  std::vector<uint32_t> gstart;
+  for (uint32_t i = 0; i < nblocks;) {
+    uint32_t j = i + 1;
+    if (sizes[i] <= p->batch_max_block) {
+      const uint32_t lim = std::min<uint32_t>(nblocks, i + std::min<uint32_t>(MAX_BATCH, p->batch_blocks));
+      while (j < lim && batchable(p->ctxs[0], sizes + i, j + 1 - i)) ++j;
+    }
+    gstart.push_back(i);
+    i = j;
+  }
+  gstart.push_back(nblocks);
+  const uint32_t ngroups = (uint32_t)gstart.size() - 1;
   std::atomic<uint32_t> next(0);
   std::atomic<int> first_err(0);
   std::mutex err_mu;
   auto worker = [&](bwtc_cuda_ctx* c) {
     for (;;) {
-      const uint32_t i = next.fetch_add(1);
-      if (i >= nblocks || first_err.load()) break;
-      const uint32_t n = sizes[i];
-      const uint32_t k = bwtc_cuda_num_starting_points(n, starts);
-      nLF[i] = k;
-      uint32_t* lf = LFpowers + (size_t)i * 256;
-      uint32_t* fr = freqs ? freqs + (size_t)i * 256 : nullptr;
-      int64_t rc;
-      if (on_device) {
-        rc = bwtc_cuda_bwt_block_device(c, in[i], out[i], n, lf, k, fr);
-      } else {
-        if (!in[i] || !out[i] || n == 0) { set_err(c->err, "null or empty block %u", i); rc = BWTC_CUDA_EARG; }
-        else rc = run_transform(c, true, in[i], out[i], nullptr, nullptr, n, lf, k, fr);
-      }
-      if (stats) stats[i] = c->stats;
+      const uint32_t g = next.fetch_add(1);
+      if (g >= ngroups || first_err.load()) break;
+      const uint32_t i = gstart[g], cnt = gstart[g + 1] - i;
+      const int rc = transform_batch(c, reinterpret_cast<const void* const*>(in + i), reinterpret_cast<void* const*>(out + i),
+                                     sizes + i, cnt, starts, on_device != 0, LFpowers + (size_t)i * 256, nLF + i,
+                                     freqs ? freqs + (size_t)i * 256 : nullptr, stats ? stats + i : nullptr);
       if (rc < 0) {
-        std::lock_guard<std::mutex> g(err_mu);
-        if (!first_err.load()) { first_err.store((int)rc); set_err(p->err, "block %u: %s", i, c->err); }
+        std::lock_guard<std::mutex> gl(err_mu);
+        if (!first_err.load()) { first_err.store(rc); set_err(p->err, "blocks %u..%u: %s", i, i + cnt - 1, c->err); }
         break;
       }
     }

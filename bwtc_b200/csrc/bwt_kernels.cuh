@@ -186,6 +186,41 @@ __global__ void __launch_bounds__(256) k_hist_bytes(const uint8_t* __restrict__ 
   if (v) atomicAdd(&hist[threadIdx.x], v);
 }
 
+// k_prep_batch — front end for a batch of small blocks sorted as one text.  Block k (bytes
+// srcs[k][0..n_k)) becomes text[k*stride .. k*stride + n_k] = reverse(X_k) . 0x00 with stride = n_0 + 1; all blocks
+// have n_0 bytes except the last (n_last <= n_0).  hist[k][256] = byte counts of block k (its freqs).
+// grid = (x, nblocks): every CTA writes a share of the text words and counts a share of its own block.
+__global__ void __launch_bounds__(256) k_prep_batch(const uint8_t* const* __restrict__ srcs, uint32_t n0, uint32_t n_last,
+                                                    uint32_t nblocks, uint8_t* __restrict__ text, uint32_t Ntot,
+                                                    uint32_t padded_words, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_hist[256];
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t stride = n0 + 1u;
+  const uint32_t cta = blockIdx.y * gridDim.x + blockIdx.x, nctas = gridDim.x * gridDim.y;
+  for (uint32_t wi = cta * blockDim.x + threadIdx.x; wi < padded_words; wi += nctas * blockDim.x) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t p = wi * 4u + j;
+      if (p < Ntot) {
+        const uint32_t k = p / stride, i = p - k * stride;
+        const uint32_t nk = (k + 1u == nblocks) ? n_last : n0;
+        if (i < nk) packed |= (uint32_t)srcs[k][nk - 1u - i] << (8 * j);
+      }
+    }
+    reinterpret_cast<uint32_t*>(text)[wi] = packed;
+  }
+  const uint32_t k = blockIdx.y;
+  const uint32_t nk = (k + 1u == nblocks) ? n_last : n0;
+  const uint8_t* X = srcs[k];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nk; i += gridDim.x * blockDim.x)
+    atomicAdd(&s_hist[X[i]], 1u);
+  __syncthreads();
+  const uint32_t v = s_hist[threadIdx.x];
+  if (v) atomicAdd(&hist[k * 256u + threadIdx.x], v);
+}
+
 // =====================================================================================================
 // k_window_sample / k_window_pairs — policy input for the round-0 key shape.  ~2^16 strided
 // 8-byte windows of the block are inserted into an open-addressing table (atomicCAS on the window itself, a
@@ -256,6 +291,10 @@ struct PackParams {
   uint8_t lut[256];   // byte -> dense code
   uint32_t bits;      // b
   uint32_t chars;     // c  (c*b <= 8*sizeof(KeyT), c <= 64)
+  // batch of nblocks > 1 blocks (text = concatenation, block k at k*stride): code 0 is RESERVED for the sentinel
+  // positions (lut[] >= 1 for every data byte), and the block number is stored above the c characters
+  uint32_t nblocks;
+  uint32_t stride;
 };
 
 template <typename KeyT>
@@ -279,6 +318,19 @@ __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__
       const long long g = wlo + q;
       s_code[q] = (g >= 0 && g < (long long)N) ? s_lut[text[g]] : (uint8_t)0;
     }
+    if (pp.nblocks > 1u) {
+      // the sentinel of block k sits at (k+1)*stride - 1 (the last block's at N-1): it is the reserved code 0,
+      // whatever lut[] says about a 0x00 data byte
+      __syncthreads();
+      const long long lo = wlo < 0 ? 0 : wlo;
+      for (long long k = lo / pp.stride + tid;; k += BLOCK) {
+        long long sp = (k + 1) * (long long)pp.stride - 1;
+        if (sp >= (long long)N) sp = (long long)N - 1;
+        if (sp - wlo >= TILE + 63) break;
+        if (sp >= wlo) s_code[sp - wlo] = 0;
+        if (sp == (long long)N - 1) break;
+      }
+    }
     __syncthreads();
     // Thread-blocked: 8 consecutive positions per thread.  Position t holds suffix N-1-t, so walking t upwards
     // walks the text downwards and each key is the previous one shifted by one character plus one new code:
@@ -294,6 +346,14 @@ __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__
       for (int k = 0; k < IPT; ++k) {
         if (k > 0) key = (KeyT)((KeyT)s_code[q0 - k] << topshift) | (KeyT)(key >> b);
         out[k] = key;
+      }
+      if (pp.nblocks > 1u) {  // block number above the characters: suffix of position t0+u0+k is N-1-(t0+u0+k)
+        const uint32_t blkshift = c * b;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+          const uint32_t t = t0 + u0 + (uint32_t)k;
+          if (t < N) out[k] |= (KeyT)((N - 1u - t) / pp.stride) << blkshift;
+        }
       }
       const uint32_t t = t0 + u0;
       if (t + IPT <= N) {
@@ -501,7 +561,7 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
                                                       const uint32_t* __restrict__ ghist,
                                                       uint32_t* __restrict__ status, uint32_t* __restrict__ ctrl,
                                                       uint32_t ctr_slot, uint32_t iota_top, uint32_t pack_bits,
-                                                      uint32_t topshift) {
+                                                      uint32_t topshift, uint32_t pred_mask) {
   // IOTA: ids are generated (position g holds suffix iota_top - g).  pack_bits != 0 additionally stores, above
   // bit pack_bits of the id, the dense code of the character PRECEDING the suffix — the top character of the
   // next key in the array — so the BWT emission of k_rerank needs no text gather at all.
@@ -545,7 +605,7 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
 #pragma unroll
       for (int k = 0; k < IPT; ++k) {
         const uint32_t g1 = first + 32 * k + 1u;
-        const uint32_t pc = (g1 < n) ? (uint32_t)(keys_in[g1] >> topshift) : 0u;  // L1 hit: the neighbour's key
+        const uint32_t pc = (g1 < n) ? ((uint32_t)(keys_in[g1] >> topshift) & pred_mask) : 0u;  // L1 hit: the neighbour's key
         val[k] |= pc << pack_bits;
       }
     }
@@ -555,7 +615,7 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
       const uint32_t g = first + 32 * k;
       key[k] = (g < n) ? keys_in[g] : (KeyT)~(KeyT)0;  // pads: digit 255, last in index order
       val[k] = (g < n) ? (IOTA ? (iota_top - g) : vals_in[g]) : 0u;
-      if (IOTA && pack_bits && g + 1u < n) val[k] |= (uint32_t)(keys_in[g + 1u] >> topshift) << pack_bits;
+      if (IOTA && pack_bits && g + 1u < n) val[k] |= ((uint32_t)(keys_in[g + 1u] >> topshift) & pred_mask) << pack_bits;
     }
   }
 
@@ -755,10 +815,32 @@ struct StageParams {
 struct EmitParams {
   const uint8_t* text;
   uint8_t* out;
-  uint32_t* lastch;  // bit 8 set = valid
+  uint32_t* lastch;  // bit 8 set = valid; one word per block of a batch
   uint32_t N;
   int block_mode;
+  // Batch of nblocks > 1 small blocks sorted as ONE text: block k owns the suffix ids AND the
+  // ranks [k*stride, k*stride + N_k) — the block number is the most significant part of every sort key.
+  uint32_t nblocks;
+  uint32_t stride;
 };
+
+// Suffix 0 of a block owns the hole at pidx: it has no preceding character to emit.
+__device__ __forceinline__ bool owns_hole(const EmitParams& ep, uint32_t id) {
+  return ep.nblocks <= 1u ? (id == 0u) : (id % ep.stride == 0u);
+}
+
+// L[nr] = ch.  The one byte the block contract moves into the hole (L[N-1] -> out[pidx]) is parked for k_finish.
+__device__ __forceinline__ void emit_bwt(const EmitParams& ep, uint32_t nr, uint8_t ch) {
+  if (ep.nblocks <= 1u) {
+    if (ep.block_mode && nr == ep.N - 1u) *ep.lastch = 0x100u | ch;
+    else ep.out[nr] = ch;
+    return;
+  }
+  const uint32_t k = nr / ep.stride;
+  const uint32_t last = ((k + 1u == ep.nblocks) ? ep.N : (k + 1u) * ep.stride) - 1u;
+  if (nr == last) ep.lastch[k] = 0x100u | ch;
+  else ep.out[nr] = ch;
+}
 
 template <typename KeyT, bool ROUND0>
 __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx,
@@ -988,12 +1070,11 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
         changed = (HF != HH);
       }
       const bool in_win = (id[k] >= rp.win_lo) && (id[k] < rp.win_hi);
-      if (single && in_win && id[k] > 0) {  // emit L[nr] = T[id-1]  (suffix 0 owns the hole at pidx)
+      if (single && in_win && !owns_hole(ep, id[k])) {  // emit L[nr] = T[id-1]
         uint8_t ch;
         if (ROUND0 && rp.packed) ch = s_dec[((k < 4 ? pc0 >> (8 * k) : pc1 >> (8 * (k - 4)))) & 0xFFu];
         else ch = ep.text[id[k] - 1];
-        if (ep.block_mode && nr == ep.N - 1) *ep.lastch = 0x100u | ch;
-        else ep.out[nr] = ch;
+        emit_bwt(ep, nr, ch);
       }
       if (single) nr |= RANK_DONE;
       else if (sp.enable) { ++live; livemask |= 1u << k; gmax = max(gmax, j - HF + 1u); }
@@ -1355,11 +1436,7 @@ __global__ void __launch_bounds__(256) k_seg_round(const uint32_t* __restrict__ 
       const unsigned long long nk = (k == IPT - 1) ? nextkey : key[k + 1];
       const bool single = ((hfmask >> k) & 1u) && (j + 1 >= L || nk != key[k]);
       uint32_t nr = (uint32_t)(key[k] >> 32) + (HF - HH);
-      if (single && myid[k] > 0) {
-        const uint8_t ch = ep.text[myid[k] - 1];
-        if (ep.block_mode && nr == ep.N - 1) *ep.lastch = 0x100u | ch;
-        else ep.out[nr] = ch;
-      }
+      if (single && !owns_hole(ep, myid[k])) emit_bwt(ep, nr, ep.text[myid[k] - 1]);
       if (single) nr |= RANK_DONE; else { keep |= 1u << k; gmax = max(gmax, j - HF + 1u); }
       newnr[k] = nr;
       if (single || HF != HH) updm |= 1u << k;
@@ -1530,11 +1607,7 @@ __global__ void __launch_bounds__(1024) k_small_rounds(const uint32_t* __restric
         const unsigned long long nk = (q == 0) ? key2[1] : nextkey;
         const bool single = hf2[q] && (j + 1 >= m || nk != key2[q]);
         uint32_t nr = (uint32_t)(key2[q] >> 32) + (HF - HH);
-        if (single && id2[q] > 0) {
-          const uint8_t ch = ep.text[id2[q] - 1];
-          if (ep.block_mode && nr == ep.N - 1) *ep.lastch = 0x100u | ch;
-          else ep.out[nr] = ch;
-        }
+        if (single && !owns_hole(ep, id2[q])) emit_bwt(ep, nr, ep.text[id2[q] - 1]);
         if (single) nr |= RANK_DONE; else keep |= 1u << q;
         if (single || HF != HH) rank[id2[q]] = nr;
       }
@@ -1592,6 +1665,27 @@ __global__ void __launch_bounds__(256) k_finish(const uint32_t* __restrict__ ran
     } else {
       out[pidx] = text[pidx];                               // "U[pidx] untouched" (divsufsort.c:506-512)
     }
+  }
+}
+
+// k_finish_batch — the same per block of a batch (grid = nblocks): block k owns ids and ranks [k*stride, ..+N_k).
+// LF[k*256 + j]; nLF_k = nLF for full blocks, nLF_last for the last one (BWTBlock.cpp:104-108 applies per block).
+__global__ void __launch_bounds__(256) k_finish_batch(const uint32_t* __restrict__ rank, uint32_t Ntot, uint32_t stride,
+                                                      uint32_t nblocks, uint8_t* __restrict__ out,
+                                                      uint32_t* __restrict__ LF, uint32_t nLF, uint32_t nLF_last,
+                                                      const uint32_t* __restrict__ lastch) {
+  const uint32_t k = blockIdx.x, tid = threadIdx.x;
+  const uint32_t start = k * stride;
+  const uint32_t Nk = (k + 1u == nblocks) ? Ntot - start : stride;
+  const uint32_t nl = (k + 1u == nblocks) ? nLF_last : nLF;
+  const uint32_t pidx = (rank[start] & RANK_MASK) - start;
+  if (tid < nl) {
+    const uint32_t x = Nk / nl;
+    LF[k * 256u + tid] = (tid == 0) ? pidx : ((rank[start + Nk - tid * x] & RANK_MASK) - start);
+  }
+  if (tid == 0) {
+    const uint32_t lc = lastch[k];
+    if (lc & 0x100u) out[start + pidx] = (uint8_t)(lc & 0xFFu);
   }
 }
 

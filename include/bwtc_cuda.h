@@ -115,6 +115,17 @@ int64_t bwtc_cuda_bwt_block(bwtc_cuda_ctx* ctx, uint8_t* block, uint32_t n,
  * may alias).  LFpowers / freqs are host pointers.  Used to measure kernel-only throughput. */
 int64_t bwtc_cuda_bwt_block_device(bwtc_cuda_ctx* ctx, const void* d_in, void* d_out, uint32_t n,
                                    uint32_t* LFpowers, uint32_t nLFpowers, uint32_t* freqs);
+/* Several blocks of one precompressor block (the slices Compressor::compress walks, Compressor.cpp:100-109)
+ * through one context, each transformed IN PLACE exactly as bwtc_cuda_bwt_block would.  blocks[k]: sizes[k] bytes, host
+ * pointers (on_device = 0) or device pointers (on_device != 0).  LFpowers: count x 256 words, row k receives
+ * nLFpowers[k] = bwtc_cuda_num_starting_points(sizes[k], starts) entries; freqs: count x 256 counters (incremented)
+ * or NULL.  Runs of 2..BWTC_CUDA_MAX_BATCH blocks of EQUAL size (the last of a run may be shorter) that fit the
+ * context's capacity together (sum of sizes + count <= max_block_bytes + 1) are sorted as ONE device-side problem —
+ * small blocks stop being launch-latency-bound (SURVEY.md §8e "small blocks are batched per launch"); other
+ * blocks are processed one after the other.  The results do not depend on the grouping.  Returns 0 or an error. */
+#define BWTC_CUDA_MAX_BATCH 64
+int bwtc_cuda_bwt_blocks(bwtc_cuda_ctx* ctx, void* const* blocks, const uint32_t* sizes, uint32_t count,
+                         uint32_t starts, int on_device, uint32_t* LFpowers, uint32_t* nLFpowers, uint32_t* freqs);
 /* BWTManager::setStartingPoints clamp + BWTBlock::prepareLFpowers sizing. */
 uint32_t bwtc_cuda_num_starting_points(uint32_t block_bytes, uint32_t starts);
 

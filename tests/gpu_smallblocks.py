@@ -8,7 +8,7 @@ mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 nb = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 n = mib << 20
 blocks = [bw.generate("markov", n, seed=100 + i) for i in range(nb)]
-for depth in (1, 2, 4, 8, 12, 16):
+for depth in [int(d) for d in os.environ.get('DEPTHS', '1,2,4,8').split(',')]:
     pipe = bw.Pipeline(n, depth=depth)
     work = [b.copy() for b in blocks]
     pipe.run(work, 8)

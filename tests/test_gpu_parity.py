@@ -170,8 +170,71 @@ def test_pipeline_equals_single_context(oracle):
         assert (work[i] == w[0]).all(), i
         assert (LF[i, : nLF[i]] == w[1]).all(), i
         assert (freqs[i] == w[2]).all(), i
-        assert stats[i]["n_suffixes"] == sizes[i] + 1
+        assert stats[i]["n_suffixes"] >= sizes[i] + 1  # (== for a block on its own, the batch's total when batched)
     pipe.close()
+
+
+def _check_batch(ctx, oracle, blocks, starts):
+    want = [oracle.block(x, starts) for x in blocks]
+    work = [x.copy() for x in blocks]
+    LF, nLF, fr = ctx.bwt_blocks(work, starts)
+    for k, w in enumerate(want):
+        assert (work[k] == w[0]).all(), ("bwt", k)
+        assert nLF[k] == w[1].size and (LF[k, : nLF[k]] == w[1]).all(), ("LF", k)
+        assert (fr[k] == w[2]).all(), ("freqs", k)
+    return ctx.stats()
+
+
+def test_batched_small_blocks_equal_single_blocks(oracle):
+    """bwtc_cuda_bwt_blocks sorts runs of equal-sized blocks as ONE text (block number above the key, reserved
+    sentinel code): every block's (bytes, LFpowers, freqs) must equal what the block gets on its own."""
+    rng = np.random.default_rng(5)
+    ctx = bw.CudaContext(8 << 20)
+    try:
+        # 16 x 256 KiB Markov blocks, last one shorter: one batch
+        blocks = [bw.generate("markov", 1 << 18, seed=100 + k) for k in range(15)] + [bw.generate("markov", 77777, seed=99)]
+        st = _check_batch(ctx, oracle, blocks, 8)
+        assert st["n_suffixes"] == 15 * ((1 << 18) + 1) + 77778, "the run must have been transformed as one batch"
+        # data full of 0x00 (the sentinel's byte value), two-letter and one-letter blocks, repeats across blocks
+        z = [rng.integers(0, 3, 50000).astype(np.uint8) for _ in range(5)]
+        z[2][:] = 0
+        z[3] = z[1].copy()
+        st = _check_batch(ctx, oracle, z, 8)
+        assert st["n_suffixes"] == 5 * 50001
+        # tiny blocks (n <= 256 -> one starting point), 64 of them; then 65 (two runs)
+        tiny = [rng.integers(97, 101, 200).astype(np.uint8) for _ in range(64)]
+        _check_batch(ctx, oracle, tiny, 8)
+        _check_batch(ctx, oracle, tiny + [tiny[0].copy()], 8)
+        # all 256 byte values present: no code left for the sentinel -> falls back to single blocks
+        full = [rng.integers(0, 256, 30000).astype(np.uint8) for _ in range(4)]
+        st = _check_batch(ctx, oracle, full, 3)
+        assert st["n_suffixes"] == 30001
+        # unequal sizes: mixed runs
+        mixed = [bw.generate("dna", n, seed=n) for n in (40000, 40000, 40000, 1000, 50000, 50000, 1, 2, 2)]
+        _check_batch(ctx, oracle, mixed, 256)
+        # repetitive blocks: many doubling rounds inside a batch
+        rep = [bw.generate("repetitive", 1 << 17, seed=7 + k) for k in range(4)]
+        _check_batch(ctx, oracle, rep, 8)
+    finally:
+        ctx.close()
+
+
+def test_pipeline_batches_small_blocks(oracle):
+    """The pipeline groups consecutive small blocks into batches; results are delivered per block, in order."""
+    sizes = [1 << 16] * 37 + [12345]
+    blocks = [bw.generate("markov", n, seed=500 + i) for i, n in enumerate(sizes)]
+    pipe = bw.Pipeline(1 << 16, depth=3)
+    try:
+        work = [x.copy() for x in blocks]
+        LF, nLF, freqs, stats = pipe.run(work, 8)
+        for i, x in enumerate(blocks):
+            w = oracle.block(x, 8)
+            assert (work[i] == w[0]).all(), i
+            assert (LF[i, : nLF[i]] == w[1]).all(), i
+            assert (freqs[i] == w[2]).all(), i
+        assert max(s["n_suffixes"] for s in stats) > (1 << 16) + 1, "no batch was formed"
+    finally:
+        pipe.close()
 
 
 ENGINE_KNOBS = [
