@@ -288,6 +288,28 @@ def main_gpu(args):
             gpu_ms += st["gpu_ms"]
             alg_bytes += st["algorithmic_bytes"]
         ctx.close()
+        # ---- informational: BASELINE configs[0] block size (1 MiB Markov blocks), device-resident, through the same
+        # pipeline call; runs of small blocks are batched into one device-side sort
+        small = None
+        if world == 1:
+            try:
+                sn, sb = 1 << 20, 64
+                sp = bw.Pipeline(sn, depth=3, device=local_rank)
+                s_in = [dev_in[j // 32][(j % 32) * sn:(j % 32 + 1) * sn] for j in range(sb)]  # 1 MiB views of the blocks
+                s_out = [torch.empty(sn, dtype=torch.uint8, device=dev) for _ in range(sb)]
+                sp_in, sp_out = [t.data_ptr() for t in s_in], [t.data_ptr() for t in s_out]
+                for _ in range(2):
+                    sp.run_ptrs(sp_in, sp_out, [sn] * sb, STARTS, on_device=True, want_stats=False)
+                sp.timing_begin()
+                for _ in range(3):
+                    sp.run_ptrs(sp_in, sp_out, [sn] * sb, STARTS, on_device=True, want_stats=False)
+                sms = sp.timing_end()
+                sp.close()
+                small = {"workload": "64 x 1 MiB Markov blocks per step (BASELINE configs[0] block size), device-resident, "
+                                     "pipeline depth 3, batched 32 blocks per sort", "value": 3 * sb * sn / 1e6 / (sms / 1e3),
+                         "unit": "MB/s"}
+            except Exception as e:  # noqa: BLE001
+                small = {"error": str(e)}
         achieved = sort_bytes / 1e9 / (sort_ms / 1e3)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r01_radix_pass_traffic.json")
@@ -329,7 +351,7 @@ def main_gpu(args):
                 "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": nb * n,
                         "d2h_bytes_per_step": nb * (n + 4 * STARTS + 256 * 4)},
                 "gpu_launches": int(ltot.item()),
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "small_blocks": small,
                 "wall_ms_per_step": wall_ms_max / args.steps}
     pipe.close()
     if world > 1:
