@@ -1140,7 +1140,7 @@ int bwtc_cuda_pipeline_create(bwtc_cuda_pipeline** out, int device, int depth, u
     uint64_t target = 32ull << 20;
     if (const char* e = getenv("BWTC_BATCH_MIB")) { const long v = atol(e); target = v > 0 ? (uint64_t)v << 20 : 0; }
     const char* eb = getenv("BWTC_BATCH");
-    if ((!eb || atoi(eb) != 0) && max_block_bytes > 0 && (uint64_t)max_block_bytes * 2 <= target) {
+    if ((!eb || atoi(eb) != 0) && max_block_bytes > 0 && (uint64_t)max_block_bytes * 4 <= target) {  // blocks <= 8 MiB
       uint64_t nb = target / max_block_bytes;
       if (nb > MAX_BATCH) nb = MAX_BATCH;
       p->batch_blocks = (uint32_t)nb;
