@@ -24,6 +24,16 @@ void BWTManager::doTransform(BWTBlock& block, uint32* freqs) {  /* BWTManager.cp
   m_transformers.at(0)->doTransform(block, freqs);
 }
 
+void BWTManager::doTransform(std::vector<BWTBlock*>& blocks, uint32 (*freqs)[256]) {
+  for (size_t i = 0; i < blocks.size(); ++i) {
+    assert(!blocks[i]->isTransformed());
+    blocks[i]->prepareLFpowers(m_startingPoints);
+  }
+  CudaBWTransform* t = dynamic_cast<CudaBWTransform*>(m_transformers.at(0));
+  if (!t) throw std::logic_error("bwtc_b200::BWTManager: batched doTransform needs the CUDA transformer");
+  t->doTransform(blocks, m_startingPoints, freqs);
+}
+
 void BWTManager::setStartingPoints(uint32 startingPoints) {  /* BWTManager.cpp:60-64 */
   if (startingPoints < 1) startingPoints = 1;
   else if (startingPoints > 256) startingPoints = 256;

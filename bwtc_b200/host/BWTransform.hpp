@@ -85,6 +85,10 @@ class CudaBWTransform : public BWTransform {
   virtual void doTransform(byte* begin, uint32 length, std::vector<uint32>& LF, uint32 freqs[256]) const;
   virtual void doTransform(BWTBlock& block);                      /* fused on the device */
   virtual void doTransform(BWTBlock& block, uint32 freqs[256]);   /* fused on the device */
+  /* All slices of one precompressor block in one call (the loop of Compressor.cpp:100-109): runs of equal-sized
+   * small blocks are sorted as ONE device-side problem (bwtc_cuda_bwt_blocks).  freqs: blocks.size() x 256 counters
+   * (incremented) or NULL.  LFpowers of every block must have been sized (prepareLFpowers) by the caller. */
+  void doTransform(std::vector<BWTBlock*>& blocks, uint32 starts, uint32 (*freqs)[256]);
   virtual uint64 maxSizeInBytes(uint64 block_size) const;
   virtual uint64 maxBlockSize(uint64 memory_budget) const;
   virtual uint64 suggestedBlockSize(uint64 memory_budget) const;
@@ -110,6 +114,9 @@ class BWTManager {
   ~BWTManager();
   void doTransform(BWTBlock& block);
   void doTransform(BWTBlock& block, uint32* freqs);
+  /* batched look-ahead extension: every block gets exactly what doTransform(block, freqs)
+   * would give it; freqs = blocks.size() x 256 counters or NULL */
+  void doTransform(std::vector<BWTBlock*>& blocks, uint32 (*freqs)[256]);
   void initialize(char choice);
   void setStartingPoints(uint32 startingPoints);
   uint32 getStartingPoints() const;

@@ -96,12 +96,36 @@ void CudaBWTransform::doTransform(BWTBlock& block, uint32 freqs[256]) {
   bwtc_cuda_get_stats(m_ctx, &m_stats);
 }
 
-/* Unlike the reference engines (which return 0, Divsufsorter.hpp:67-70) these are real: ~31 bytes of device
+void CudaBWTransform::doTransform(std::vector<BWTBlock*>& blocks, uint32 starts, uint32 (*freqs)[256]) {
+  if (blocks.empty()) return;
+  /* room for a batch: up to 64 equal-sized small blocks (~32 MiB of text) are sorted as one device-side problem */
+  uint64 biggest = 0, run = 0;
+  for (size_t i = 0; i < blocks.size(); ++i) biggest = std::max<uint64>(biggest, blocks[i]->size());
+  for (size_t i = 0; i < blocks.size() && i < BWTC_CUDA_MAX_BATCH; ++i) run += (uint64)blocks[i]->size() + 1;
+  const uint64 batch_room = std::min<uint64>(run, (32ull << 20) + BWTC_CUDA_MAX_BATCH);
+  ensure((uint32)std::min<uint64>(std::max<uint64>(biggest, batch_room), BWTC_CUDA_MAX_BLOCK));
+  std::vector<void*> ptrs(blocks.size());
+  std::vector<uint32> sizes(blocks.size()), nLF(blocks.size());
+  std::vector<uint32> LF(blocks.size() * 256);
+  for (size_t i = 0; i < blocks.size(); ++i) { ptrs[i] = blocks[i]->begin(); sizes[i] = (uint32)blocks[i]->size(); }
+  const int rc = bwtc_cuda_bwt_blocks(m_ctx, &ptrs[0], &sizes[0], (uint32)blocks.size(), starts, 0, &LF[0], &nLF[0],
+                                      freqs ? &freqs[0][0] : 0);
+  if (rc < 0) fail("doTransform(blocks)", rc);
+  for (size_t i = 0; i < blocks.size(); ++i) {
+    std::vector<uint32>& dst = blocks[i]->LFpowers();
+    if (dst.size() != nLF[i]) fail("doTransform(blocks): LFpowers not sized by prepareLFpowers", BWTC_CUDA_EARG);
+    for (uint32 j = 0; j < nLF[i]; ++j) dst[j] = LF[i * 256 + j];
+    blocks[i]->setTransformed(true);
+  }
+  bwtc_cuda_get_stats(m_ctx, &m_stats);
+}
+
+/* Unlike the reference engines (which return 0, Divsufsorter.hpp:67-70) these are real: ~35 bytes of device
  * scratch per suffix plus look-back status words. */
-uint64 CudaBWTransform::maxSizeInBytes(uint64 block_size) const { return 32 * (block_size + 1) + (1u << 20); }
+uint64 CudaBWTransform::maxSizeInBytes(uint64 block_size) const { return 36 * (block_size + 1) + (1u << 20); }
 uint64 CudaBWTransform::maxBlockSize(uint64 memory_budget) const {
   if (memory_budget <= (1u << 20) + 64) return 0;
-  uint64 b = (memory_budget - (1u << 20)) / 32 - 1;
+  uint64 b = (memory_budget - (1u << 20)) / 36 - 1;
   return b > BWTC_CUDA_MAX_BLOCK ? BWTC_CUDA_MAX_BLOCK : b;
 }
 uint64 CudaBWTransform::suggestedBlockSize(uint64 memory_budget) const {

@@ -2,6 +2,7 @@
 #include <cstring>
 #include <exception>
 #include <stdexcept>
+#include <vector>
 
 #include "BWTransform.hpp"
 
@@ -31,6 +32,32 @@ int bwtc_host_manager_transform(unsigned char* buf, unsigned n, unsigned starts,
     if (!b.isTransformed()) throw std::runtime_error("block not flagged transformed");
     *nLF_out = (unsigned)b.LFpowers().size();
     for (size_t i = 0; i < b.LFpowers().size(); ++i) LF_out[i] = b.LFpowers()[i];
+    return 0;
+  } catch (const std::exception& e) {
+    if (err && errlen) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
+    return -1;
+  }
+}
+
+/* BWTManager m(starts); m.initialize('c'); m.doTransform(blocks, freqs) — the batched extension: count blocks,
+ * bufs[k] / sizes[k]; LF_out = count x 256, nLF_out = count, freqs = count x 256 or NULL. */
+int bwtc_host_manager_transform_batch(unsigned char** bufs, const unsigned* sizes, unsigned count, unsigned starts,
+                                      unsigned* LF_out, unsigned* nLF_out, unsigned* freqs, char* err, unsigned errlen) {
+  try {
+    std::vector<bwtc_b200::BWTBlock> store;
+    store.reserve(count);
+    std::vector<bwtc_b200::BWTBlock*> blocks;
+    for (unsigned k = 0; k < count; ++k) { store.push_back(bwtc_b200::BWTBlock(bufs[k], sizes[k], false)); }
+    for (unsigned k = 0; k < count; ++k) blocks.push_back(&store[k]);
+    bwtc_b200::BWTManager m(1);
+    m.setStartingPoints(starts);
+    m.initialize('c');
+    m.doTransform(blocks, reinterpret_cast<unsigned (*)[256]>(freqs));
+    for (unsigned k = 0; k < count; ++k) {
+      if (!store[k].isTransformed()) throw std::runtime_error("block not flagged transformed");
+      nLF_out[k] = (unsigned)store[k].LFpowers().size();
+      for (size_t i = 0; i < store[k].LFpowers().size(); ++i) LF_out[k * 256 + i] = store[k].LFpowers()[i];
+    }
     return 0;
   } catch (const std::exception& e) {
     if (err && errlen) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }

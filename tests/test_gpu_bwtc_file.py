@@ -66,3 +66,28 @@ def test_cpp_mirror_classes(oracle):
             assert (buf[:-1] == want[0]).all() and (LF[: k.value] == want[1]).all() and (fr == want[2]).all(), (n, via_base)
     assert lib.bwtc_host_is_valid_choice(ctypes.c_char(b"c")) == 1
     assert lib.bwtc_host_is_valid_choice(ctypes.c_char(b"d")) == 0
+
+
+def test_cpp_mirror_batched_manager(oracle):
+    """bwtc_b200::BWTManager::doTransform(std::vector<BWTBlock*>&, freqs): the slices of one precompressor block in one
+    call (batched on the device) give every block what the single-block call gives it."""
+    lib = ctypes.CDLL(bw.HOST_LIB_PATH)
+    sizes = [1 << 16] * 9 + [4321, 300, 300, 1]
+    blocks = [bw.generate(["markov", "dna", "random"][i % 3], n, seed=900 + i) for i, n in enumerate(sizes)]
+    work = [b.copy() for b in blocks]
+    count = len(work)
+    ptrs = (ctypes.c_void_p * count)(*[w.ctypes.data for w in work])
+    sz = np.array(sizes, np.uint32)
+    LF = np.zeros((count, 256), np.uint32)
+    nLF = np.zeros(count, np.uint32)
+    fr = np.zeros((count, 256), np.uint32)
+    err = ctypes.create_string_buffer(512)
+    rc = lib.bwtc_host_manager_transform_batch(ptrs, ctypes.c_void_p(sz.ctypes.data), ctypes.c_uint(count), ctypes.c_uint(8),
+                                               ctypes.c_void_p(LF.ctypes.data), ctypes.c_void_p(nLF.ctypes.data),
+                                               ctypes.c_void_p(fr.ctypes.data), err, ctypes.c_uint(512))
+    assert rc == 0, err.value
+    for i, x in enumerate(blocks):
+        w = oracle.block(x, 8)
+        assert (work[i] == w[0]).all(), i
+        assert nLF[i] == w[1].size and (LF[i, : nLF[i]] == w[1]).all(), i
+        assert (fr[i] == w[2]).all(), i
