@@ -318,3 +318,35 @@ def test_256mib_random_block_properties():
     order_by_rank = np.argsort(LF)
     order_by_text = sorted(range(8), key=lambda i: keys[i])
     assert list(order_by_rank) == order_by_text
+
+
+def test_maximum_block_size_properties():
+    """The largest block the engine accepts: BWTC_CUDA_MAX_BLOCK = 0x3FFFFFF0 bytes (N just under 2^30, 30-bit ranks
+    and look-back counters, ~40 GB of scratch).  Property check as for the 256 MiB block."""
+    n = 0x3FFFFFF0
+    try:
+        ctx = bw.CudaContext(n)
+    except bw.BwtcCudaError as e:  # a smaller GPU: not this engine's target, but do not fail the suite on it
+        pytest.skip(f"cannot allocate scratch for a 1 GiB block: {e}")
+    x = bw.generate("random", n, seed=33)
+    blk = x.copy()
+    LF = np.zeros(8, np.uint32)
+    fr = np.zeros(256, np.uint32)
+    pidx = ctx.bwt_block(blk, LF, fr)
+    st = ctx.stats()
+    ctx.close()
+    assert st["n_suffixes"] == n + 1 and pidx == LF[0]
+    hist = np.bincount(x, minlength=256)
+    assert (fr == hist).all() and (np.bincount(blk, minlength=256) == hist).all()
+    N = n + 1
+    xs = N // 8
+    pos = [0] + [N - j * xs for j in range(1, 8)]
+
+    def suffix_prefix(p):  # first 64 bytes of suffix p of T' = reverse(X) + 0x00, without materialising T'
+        idx = np.arange(p, min(p + 64, N))
+        return bytes(np.where(idx < n, x[np.minimum(n - 1 - idx, n - 1)], 0).astype(np.uint8))
+
+    keys = [suffix_prefix(p) for p in pos]
+    assert list(np.argsort(LF)) == sorted(range(8), key=lambda i: keys[i])
+    with pytest.raises(bw.BwtcCudaError):  # one byte more is refused loudly (no silent truncation, no fallback)
+        bw.CudaContext(n + 1)
