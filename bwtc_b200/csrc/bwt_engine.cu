@@ -55,37 +55,40 @@ struct bwtc_cuda_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  uint32_t cap = 0;  // max block bytes
-  // device memory
-  uint8_t* d_in = nullptr;
-  uint8_t* d_text = nullptr;
-  uint8_t* d_out = nullptr;
-  uint32_t* d_rank = nullptr;
-  void* d_keys[2] = {nullptr, nullptr};
-  uint32_t* d_idx[2] = {nullptr, nullptr};
-  uint32_t* d_zero = nullptr;  // [ctrl CTR_WORDS][hist HIST_WORDS][tstate 2*max_aux_tiles] zeroed per round
-  uint32_t* d_status = nullptr;  // [MAX_PASSES][max_rs_tiles][256]
-  uint32_t* d_LF = nullptr;       // [LF_PARK) LFpowers (one row of 256 per block of a batch), [LF_PARK + k] parked hole byte
-                                  // of block k, [LF_WATCH] watchdog word of k_small_rounds
-  uint32_t* d_bhist = nullptr;    // [MAX_BATCH][256] per-block byte histograms of a batch
-  const uint8_t** d_bptr = nullptr;  // [MAX_BATCH] device pointers to the blocks of a batch
-  uint8_t* h_batch = nullptr;     // pinned: [MAX_BATCH] pointers, [MAX_BATCH][256] histograms, [MAX_BATCH][256] LFpowers
+  uint32_t cap = 0;  // max block bytes (a batch: sum of block bytes + blocks - 1)
+  size_t max_rs_tiles = 0, max_aux_tiles = 0;
+  // ---- device memory
+  uint8_t* d_in = nullptr;        // staged input block(s); scratch once the text exists
+  uint8_t* d_text = nullptr;      // T' = reverse(X) . 0x00 (+ padding)
+  uint8_t* d_out = nullptr;       // BWT bytes by rank
+  uint32_t* d_rank = nullptr;     // inverse suffix array, bit 31 = final
+  void* d_keys[2] = {nullptr, nullptr};      // ping-pong sort keys (8N bytes each); between sorts: 2 x 2 u32[N] work arrays
+  uint32_t* d_idx[2] = {nullptr, nullptr};   // ping-pong suffix ids; between sorts: 2 u32[N] work arrays
+  uint32_t* d_scat = nullptr;     // u32[N]: staged ranks of the bucketed scatter (the ids go to the idle id buffer)
+  uint32_t* d_zero = nullptr;     // [ctrl CTR_WORDS][hist HIST_WORDS][tstate rows of max_aux_tiles] zeroed per round
+  uint32_t* d_status = nullptr;   // [MAX_PASSES][max_rs_tiles][256] radix look-back words
   uint32_t* d_tilecnt = nullptr;  // [2][max_aux_tiles]: per-tile live counts of k_rerank and their exclusive prefix,
                                   // then [max_aux_tiles][MAX_RERANK_WINDOWS+1] bucket offsets of the bucketed scatter
-  uint32_t* d_scat = nullptr;     // u32[N]: staged ranks of the bucketed scatter (the ids go to the idle id buffer)
-  int use_batch = 1;              // small equal-sized blocks of one call are sorted as one text (BWTC_BATCH=0: never)
-  int use_pack_pred = 1;          // carry code(T[id-1]) above the id through the round-0 sort when it fits
-  int bucket_min_windows = 3;     // bucketed scatter from this many L2 windows on (0 = never)
+  uint32_t* d_LF = nullptr;       // [LF_PARK) LFpowers (one row of 256 per block of a batch), [LF_PARK + k] parked hole byte
+                                  // of block k, [LF_WATCH] watchdog word of k_small_rounds
   unsigned long long* d_wtab = nullptr;  // window-sample table: WS_SLOTS keys, WS_SLOTS counters, 2 doubles
-  size_t max_rs_tiles = 0, max_aux_tiles = 0;
-  // pinned host
-  uint32_t* h_small = nullptr;  // [ctrl CTR_WORDS][hist HIST_WORDS][LF 256]
+  uint32_t* d_bhist = nullptr;    // [MAX_BATCH][256] per-block byte histograms of a batch
+  const uint8_t** d_bptr = nullptr;  // [MAX_BATCH] device pointers to the blocks of a batch
+  // ---- pinned host memory
+  uint32_t* h_small = nullptr;    // [ctrl CTR_WORDS][hist HIST_WORDS][LF 256 + pair statistics]
+  uint8_t* h_batch = nullptr;     // [MAX_BATCH] pointers, [MAX_BATCH][256] histograms, [MAX_BATCH][256] LFpowers
+  // ---- timing
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   int timing_detail = 0;
-  int use_seg = 1;  // segmented (sort-free) doubling rounds when every group is small
-  uint32_t force_chars = 0, force_keybytes = 0;
+  // ---- policy knobs (defaults are the measured optimum on B200; the environment variables in bwtc_cuda_ctx_create
+  //      exist so that tests can force every code path, see tests/test_gpu_parity.py)
+  int use_seg = 1;                // segmented (sort-free) doubling rounds when every group is small
+  int use_batch = 1;              // small equal-sized blocks of one call are sorted as one text
+  int use_pack_pred = 1;          // carry code(T[id-1]) above the id through the round-0 sort when it fits
+  int bucket_min_windows = 3;     // bucketed rank scatter from this many L2 windows on (0 = never)
   uint64_t rerank_window_bytes = 72ull << 20;  // rank-scatter window kept L2-resident (126 MB L2)
+  uint32_t force_chars = 0, force_keybytes = 0;
   uint32_t debug_max_rounds = 0;  // != 0: stop refining after this many rounds (results are then wrong on purpose)
   int last_cur = 0;               // sort buffer holding the last round's sorted records
   bwtc_cuda_stats stats;
