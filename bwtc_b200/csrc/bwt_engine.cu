@@ -633,8 +633,9 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   };
 
   // ---- doubling rounds
-  const int lo_bits = (int)ceil_log2_u64((uint64_t)N + 1);
-  const int hi_bits = (int)ceil_log2_u64((uint64_t)N);
+  const int lo_bits = (int)ceil_log2_u64((uint64_t)N + 1);  // rank[i+h] + 1 in [0, N]
+  // high part = (rank of the group head) >> 1 (k_build_keys): heads of live groups are <= N - 2
+  const int hi_bits = N > 3 ? (int)ceil_log2_u64((((uint64_t)N - 2) >> 1) + 1) : 1;
   const uint32_t npassd = div_up((uint64_t)(lo_bits + hi_bits), 8);
   const uint32_t maskd = (1u << npassd) - 1u;
   uint64_t h = pl.chars;

@@ -510,9 +510,12 @@ __global__ void __launch_bounds__(256) k_build_keys(const uint32_t* __restrict__
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       if ((livemask >> k) & 1u) {
-        const unsigned long long key = ((unsigned long long)r[k] << lo_bits) | (unsigned long long)r2[k];
+        // high part = rank >> 1: a live group has >= 2 members, so the heads of two live groups differ by >= 2 and
+        // rank >> 1 still identifies (and orders) the group; the dropped bit rides in bit 31 of the id payload
+        // (ids are < 2^30).  One bit less per key is one digit pass less per round at N = 2^k + 1.
+        const unsigned long long key = ((unsigned long long)(r[k] >> 1) << lo_bits) | (unsigned long long)r2[k];
         keys[pos] = key;
-        idx[pos] = i0 + k;
+        idx[pos] = (i0 + k) | ((r[k] & 1u) << 31);
         ++pos;
         for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + (uint32_t)((key >> (8 * p)) & 0xFF)], 1u);
       }
@@ -911,6 +914,14 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
       id[k] &= rp.id_mask;
     }
   }
+  uint32_t lowbits = 0;  // rounds >= 1: bit 0 of each record's old rank travels in bit 31 of the id (k_build_keys)
+  if (!ROUND0) {
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      lowbits |= (id[k] >> 31) << k;
+      id[k] &= 0x7FFFFFFFu;
+    }
+  }
   // hand the last key (and its "short" flag) of every thread to its right neighbour
   s_lastkey[tid] = key[IPT - 1];
   if (ROUND0) s_lastshort[tid] = (j0 + IPT - 1 < m && id[IPT - 1] >= rp.short_thresh) ? 1u : 0u;
@@ -1066,7 +1077,7 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
         changed = true;
       } else {
         const uint32_t HH = max(lh[k], exh) - 1u;
-        nr = (uint32_t)(key[k] >> rp.lo_bits) + (HF - HH);
+        nr = (((uint32_t)(key[k] >> rp.lo_bits) << 1) | ((lowbits >> k) & 1u)) + (HF - HH);
         changed = (HF != HH);
       }
       const bool in_win = (id[k] >= rp.win_lo) && (id[k] < rp.win_hi);
@@ -1245,9 +1256,9 @@ __global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restr
     const uint32_t i = list[j];
     const uint32_t r = rank[i] & RANK_MASK;
     const uint32_t r2 = (h < N - i) ? ((rank[i + h] & RANK_MASK) + 1u) : 0u;
-    const unsigned long long key = ((unsigned long long)r << lo_bits) | (unsigned long long)r2;
+    const unsigned long long key = ((unsigned long long)(r >> 1) << lo_bits) | (unsigned long long)r2;  // see k_build_keys
     keys[j] = key;
-    idx[j] = i;
+    idx[j] = i | ((r & 1u) << 31);
     for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + (uint32_t)((key >> (8 * p)) & 0xFF)], 1u);
   }
   __syncthreads();
