@@ -64,6 +64,7 @@ struct bwtc_cuda_ctx {
   uint32_t* d_rank = nullptr;     // inverse suffix array, bit 31 = final
   void* d_keys[2] = {nullptr, nullptr};      // ping-pong sort keys (8N bytes each); between sorts: 2 x 2 u32[N] work arrays
   uint32_t* d_idx[2] = {nullptr, nullptr};   // ping-pong suffix ids; between sorts: 2 u32[N] work arrays
+  uint8_t* d_aux[2] = {nullptr, nullptr};    // ping-pong one-byte payload of the round-0 sort (predecessor codes), N each
   uint32_t* d_scat = nullptr;     // u32[N]: staged ranks of the bucketed scatter (the ids go to the idle id buffer)
   uint32_t* d_zero = nullptr;     // [ctrl CTR_WORDS][hist HIST_WORDS][tstate rows of max_aux_tiles] zeroed per round
   uint32_t* d_status = nullptr;   // [MAX_PASSES][max_rs_tiles][256] radix look-back words
@@ -86,6 +87,7 @@ struct bwtc_cuda_ctx {
   int use_seg = 1;                // segmented (sort-free) doubling rounds when every group is small
   int use_batch = 1;              // small equal-sized blocks of one call are sorted as one text
   int use_pack_pred = 1;          // carry code(T[id-1]) above the id through the round-0 sort when it fits
+  uint32_t aux_min_suffixes = 96u << 20;  // ... else, from this many suffixes on, as a one-byte payload array (0 = never)
   int bucket_min_windows = 3;     // bucketed rank scatter from this many L2 windows on (0 = never)
   uint64_t rerank_window_bytes = 72ull << 20;  // rank-scatter window kept L2-resident (126 MB L2)
   uint32_t force_chars = 0, force_keybytes = 0;
@@ -113,10 +115,10 @@ struct bwtc_cuda_ctx {
 
 namespace {
 
-template <typename KeyT, int IPT, bool IOTA>
+template <typename KeyT, int IPT, bool IOTA, bool AUX>
 int set_pass_attr(bwtc_cuda_ctx* ctx) {
-  CK(ctx, cudaFuncSetAttribute(k_radix_pass<KeyT, RS_BLOCK, IPT, IOTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)RadixPassSmem<KeyT, RS_BLOCK, IPT>::bytes));
+  CK(ctx, cudaFuncSetAttribute(k_radix_pass<KeyT, RS_BLOCK, IPT, IOTA, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)RadixPassSmem<KeyT, RS_BLOCK, IPT, AUX>::bytes));
   return 0;
 }
 
@@ -127,7 +129,7 @@ void ctx_free(bwtc_cuda_ctx* c) {
   cudaFree(c->d_in); cudaFree(c->d_text); cudaFree(c->d_out); cudaFree(c->d_rank);
   cudaFree(c->d_keys[0]); cudaFree(c->d_keys[1]); cudaFree(c->d_idx[0]); cudaFree(c->d_idx[1]);
   cudaFree(c->d_zero); cudaFree(c->d_status); cudaFree(c->d_LF); cudaFree(c->d_wtab); cudaFree(c->d_tilecnt); cudaFree(c->d_scat);
-  cudaFree(c->d_bhist); cudaFree(c->d_bptr);
+  cudaFree(c->d_bhist); cudaFree(c->d_bptr); cudaFree(c->d_aux[0]); cudaFree(c->d_aux[1]);
   if (c->h_batch) cudaFreeHost(c->h_batch);
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -250,13 +252,12 @@ struct PassTimer {
 
 // One LSD radix sort of m records: executes the digit passes whose bit is set in pass_mask, ping-ponging
 // between buffer 0 and 1.  Records start in buffer `cur` (0); returns the buffer holding the result.
-template <typename KeyT, int IPT>
-int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota, uint32_t iota_top, int* cur_io,
-             PassTimer* pt, uint32_t* passes_done, uint32_t pack_bits = 0, uint32_t topshift = 0,
-             uint32_t pred_mask = 0xFFFFFFFFu) {
+template <typename KeyT, int IPT, bool AUX>
+int run_sort_impl(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota, uint32_t iota_top, int* cur_io,
+                  PassTimer* pt, uint32_t* passes_done, uint32_t pack_bits, uint32_t topshift, uint32_t pred_mask) {
   constexpr uint32_t TILE = RS_BLOCK * IPT;
   const uint32_t tiles = div_up(m, TILE);
-  const size_t smem = RadixPassSmem<KeyT, RS_BLOCK, IPT>::bytes;
+  const size_t smem = RadixPassSmem<KeyT, RS_BLOCK, IPT, AUX>::bytes;
   int cur = *cur_io;
   bool iota = first_iota;
   uint32_t done = 0;
@@ -267,19 +268,19 @@ int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota
     uint32_t* status = ctx->d_status + (size_t)p * ctx->max_rs_tiles * 256u;
     if (pt->begin()) return BWTC_CUDA_ECUDA;
     if (iota)
-      k_radix_pass<KeyT, RS_BLOCK, IPT, true><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
+      k_radix_pass<KeyT, RS_BLOCK, IPT, true, AUX><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-          CTR_PASS0 + p, iota_top, pack_bits, topshift, pred_mask);
+          CTR_PASS0 + p, iota_top, pack_bits, topshift, pred_mask, nullptr, ctx->d_aux[cur ^ 1]);
     else
-      k_radix_pass<KeyT, RS_BLOCK, IPT, false><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
+      k_radix_pass<KeyT, RS_BLOCK, IPT, false, AUX><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, ctx->d_idx[cur], kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-          CTR_PASS0 + p, iota_top, 0u, 0u, 0u);
+          CTR_PASS0 + p, iota_top, 0u, 0u, 0u, ctx->d_aux[cur], ctx->d_aux[cur ^ 1]);
     CK(ctx, cudaGetLastError());
     if (pt->end()) return BWTC_CUDA_ECUDA;
     ctx->stats.kernel_launches++;
-    const uint64_t rec = sizeof(KeyT) + 4;
-    ctx->stats.algorithmic_bytes += (uint64_t)m * (2 * rec - (iota ? 4 : 0));
-    ctx->stats.sort_bytes += (uint64_t)m * (2 * rec - (iota ? 4 : 0));
+    const uint64_t rec = sizeof(KeyT) + 4 + (AUX ? 1 : 0);
+    ctx->stats.algorithmic_bytes += (uint64_t)m * (2 * rec - (iota ? 4 + (AUX ? 1 : 0) : 0));
+    ctx->stats.sort_bytes += (uint64_t)m * (2 * rec - (iota ? 4 + (AUX ? 1 : 0) : 0));
     ctx->stats.sort_launches++;
     iota = false;
     cur ^= 1;
@@ -288,6 +289,20 @@ int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota
   *cur_io = cur;
   *passes_done = done;
   return 0;
+}
+
+// One LSD radix sort of m records: executes the digit passes whose bit is set in pass_mask, ping-ponging
+// between buffer 0 and 1.  Records start in buffer `cur` (0); returns the buffer holding the result.
+// aux: a one-byte payload (predecessor character code) is produced by the first pass and carried along.
+template <typename KeyT, int IPT>
+int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota, uint32_t iota_top, int* cur_io,
+             PassTimer* pt, uint32_t* passes_done, uint32_t pack_bits = 0, uint32_t topshift = 0,
+             uint32_t pred_mask = 0xFFFFFFFFu, bool aux = false) {
+  if (aux)
+    return run_sort_impl<KeyT, IPT, true>(ctx, m, pass_mask, first_iota, iota_top, cur_io, pt, passes_done, pack_bits, topshift,
+                                          pred_mask);
+  return run_sort_impl<KeyT, IPT, false>(ctx, m, pass_mask, first_iota, iota_top, cur_io, pt, passes_done, pack_bits, topshift,
+                                         pred_mask);
 }
 
 int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m, uint32_t rs_tile, uint32_t pass_mask) {
@@ -565,12 +580,15 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   const bool pack_pred = ctx->use_pack_pred && (id_bits + pl.bits <= 32) && (mask0 & 1u);
   const uint32_t topshift = (pl.chars - 1) * pl.bits;
   const uint32_t pred_mask = (1u << pl.bits) - 1u;  // (a batch key carries the block number above the characters)
+  // No spare id bits (byte alphabets above 16 MiB) and a text too large for an L2-resident gather at emission time:
+  // the predecessor codes travel as a one-byte payload array instead.
+  const bool aux_pred = !pack_pred && ctx->aux_min_suffixes && N >= ctx->aux_min_suffixes && (mask0 & 1u) && !bs;
   if (pl.keybytes == 4)
     rc = run_sort<uint32_t, RS_IPT32>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone, pack_pred ? id_bits : 0u, topshift,
-                                      pred_mask);
+                                      pred_mask, aux_pred);
   else
     rc = run_sort<unsigned long long, RS_IPT64>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone, pack_pred ? id_bits : 0u,
-                                                topshift, pred_mask);
+                                                topshift, pred_mask, aux_pred);
   if (rc) return rc;
   const size_t round0_events = pt.used;
   S.sort0_launches = S.sort_launches;
@@ -587,7 +605,8 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       rp.short_thresh = pl.chars > text_end ? 0u : text_end - pl.chars + 1u;
     }
     rp.lo_bits = 0;
-    rp.packed = pack_pred ? 1u : 0u;
+    rp.packed = pack_pred ? 1u : (aux_pred ? 2u : 0u);
+    rp.pred_aux = ctx->d_aux[cur];
     rp.id_bits = pack_pred ? id_bits : 31u;
     rp.id_mask = pack_pred ? (uint32_t)((1ull << id_bits) - 1ull) : 0xFFFFFFFFu;
     memset(rp.decode, 0, sizeof(rp.decode));
@@ -736,6 +755,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       rp.short_thresh = 0;
       rp.lo_bits = lo_bits;
       rp.packed = 0;
+      rp.pred_aux = nullptr;
       rp.id_bits = 31;
       rp.id_mask = 0xFFFFFFFFu;
       rc = launch_rerank<unsigned long long, false>(ctx, cur, m, N, rp, ep, pool[2 * (cur ^ 1)], pool[2 * (cur ^ 1) + 1]);
@@ -912,6 +932,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (const char* e = getenv("BWTC_SEG")) c->use_seg = atoi(e);
   if (const char* e = getenv("BWTC_BATCH")) c->use_batch = atoi(e);
   if (const char* e = getenv("BWTC_PACK_PRED")) c->use_pack_pred = atoi(e);
+  if (const char* e = getenv("BWTC_AUX_MIN_MIB")) { const long v = atol(e); c->aux_min_suffixes = v > 0 ? (uint32_t)v << 20 : (v == 0 ? 1u : 0u); }
   if (const char* e = getenv("BWTC_BUCKET_MIN_WINDOWS")) c->bucket_min_windows = atoi(e);
   if (const char* e = getenv("BWTC_RERANK_WINDOW_MB")) { long v = atol(e); if (v > 0) c->rerank_window_bytes = (uint64_t)v << 20; }
   c->err[0] = 0;
@@ -952,6 +973,8 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_wtab, (size_t)WS_SLOTS * 12 + 64);
   ALLOC(c->d_tilecnt, (size_t)c->max_aux_tiles * (2 + MAX_RERANK_WINDOWS + 1) * 4 + 64);
   ALLOC(c->d_scat, (size_t)N * 4 + 64);
+  ALLOC(c->d_aux[0], padded);
+  ALLOC(c->d_aux[1], padded);
 #undef ALLOC
   if (!rc) {
     e = cudaMallocHost((void**)&c->h_small, (size_t)(CTR_WORDS + HIST_WORDS + 256 + 8) * 4);
@@ -964,10 +987,14 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   }
   if (!rc) {
     int r2 = 0;
-    r2 |= set_pass_attr<uint32_t, RS_IPT32, true>(c);
-    r2 |= set_pass_attr<uint32_t, RS_IPT32, false>(c);
-    r2 |= set_pass_attr<unsigned long long, RS_IPT64, true>(c);
-    r2 |= set_pass_attr<unsigned long long, RS_IPT64, false>(c);
+    r2 |= set_pass_attr<uint32_t, RS_IPT32, true, false>(c);
+    r2 |= set_pass_attr<uint32_t, RS_IPT32, false, false>(c);
+    r2 |= set_pass_attr<unsigned long long, RS_IPT64, true, false>(c);
+    r2 |= set_pass_attr<unsigned long long, RS_IPT64, false, false>(c);
+    r2 |= set_pass_attr<uint32_t, RS_IPT32, true, true>(c);
+    r2 |= set_pass_attr<uint32_t, RS_IPT32, false, true>(c);
+    r2 |= set_pass_attr<unsigned long long, RS_IPT64, true, true>(c);
+    r2 |= set_pass_attr<unsigned long long, RS_IPT64, false, true>(c);
     if (r2) { set_err(g_err, "%s", c->err); rc = BWTC_CUDA_ECUDA; }
   }
   if (rc) { ctx_free(c); return rc; }

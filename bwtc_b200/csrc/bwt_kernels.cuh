@@ -549,14 +549,18 @@ __device__ unsigned long long* g_prof_buf = nullptr;  // [tiles][16] SM-clock st
 #define BWTC_PROF(k) do { } while (0)
 #endif
 
-template <typename KeyT, int BLOCK, int IPT>
+template <typename KeyT, int BLOCK, int IPT, bool AUX = false>
 struct RadixPassSmem {
   static constexpr int TILE = BLOCK * IPT;
   static constexpr int WARPS = BLOCK / 32;
-  static constexpr size_t bytes = (sizeof(KeyT) + 4) * TILE + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 32);
+  static constexpr size_t bytes =
+      (sizeof(KeyT) + 4) * TILE + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 32) + (AUX ? TILE : 0);
 };
 
-template <typename KeyT, int BLOCK, int IPT, bool IOTA>
+// AUX: a third, one-byte payload travels with every record — the dense code of the character preceding the
+// suffix, for blocks whose id has no spare bits for it (pack_bits) and whose text is too large for an L2-resident
+// gather at emission time.  The IOTA pass produces it (top character of the next key), later passes carry it.
+template <typename KeyT, int BLOCK, int IPT, bool IOTA, bool AUX = false>
 __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* __restrict__ keys_in,
                                                       const uint32_t* __restrict__ vals_in,
                                                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
@@ -564,7 +568,9 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
                                                       const uint32_t* __restrict__ ghist,
                                                       uint32_t* __restrict__ status, uint32_t* __restrict__ ctrl,
                                                       uint32_t ctr_slot, uint32_t iota_top, uint32_t pack_bits,
-                                                      uint32_t topshift, uint32_t pred_mask) {
+                                                      uint32_t topshift, uint32_t pred_mask,
+                                                      const uint8_t* __restrict__ aux_in = nullptr,
+                                                      uint8_t* __restrict__ aux_out = nullptr) {
   // IOTA: ids are generated (position g holds suffix iota_top - g).  pack_bits != 0 additionally stores, above
   // bit pack_bits of the id, the dense code of the character PRECEDING the suffix — the top character of the
   // next key in the array — so the BWT emission of k_rerank needs no text gather at all.
@@ -578,6 +584,7 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
   uint32_t* s_binbase = s_whist + WARPS * 256;
   uint32_t* s_texcl = s_binbase + 256;
   uint32_t* s_misc = s_texcl + 256;  // [0] tile id, [8..15] scan scratch
+  uint8_t* s_aux = reinterpret_cast<uint8_t*>(s_misc + 32);  // AUX: bytes staged beside keys and ids
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef BWTC_PROFILE_STAGES
@@ -598,6 +605,9 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
   // ---- load (warp-striped)
   KeyT key[IPT];
   uint32_t val[IPT];
+  uint32_t aux[AUX ? IPT / 4 : 1];  // one byte per record, four to a register
+#pragma unroll
+  for (int q = 0; q < (AUX ? IPT / 4 : 1); ++q) aux[q] = 0;
   const uint32_t first = tile_base + warp * (32 * IPT) + lane;
   if (valid == (uint32_t)TILE) {
 #pragma unroll
@@ -612,6 +622,16 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
         val[k] |= pc << pack_bits;
       }
     }
+    if (AUX) {
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        const uint32_t g = first + 32 * k;
+        uint32_t a;
+        if (IOTA) a = (g + 1u < n) ? ((uint32_t)(keys_in[g + 1u] >> topshift) & pred_mask) : 0u;
+        else a = aux_in[g];
+        aux[k / 4] |= a << (8 * (k % 4));
+      }
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
@@ -619,6 +639,12 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
       key[k] = (g < n) ? keys_in[g] : (KeyT)~(KeyT)0;  // pads: digit 255, last in index order
       val[k] = (g < n) ? (IOTA ? (iota_top - g) : vals_in[g]) : 0u;
       if (IOTA && pack_bits && g + 1u < n) val[k] |= ((uint32_t)(keys_in[g + 1u] >> topshift) & pred_mask) << pack_bits;
+      if (AUX) {
+        uint32_t a = 0;
+        if (IOTA) a = (g + 1u < n) ? ((uint32_t)(keys_in[g + 1u] >> topshift) & pred_mask) : 0u;
+        else if (g < n) a = aux_in[g];
+        aux[k / 4] |= a << (8 * (k % 4));
+      }
     }
   }
 
@@ -683,6 +709,7 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
     const uint32_t p = my_hist[d] + lpos[k];
     s_keys[p] = key[k];
     s_vals[p] = val[k];
+    if (AUX) s_aux[p] = (uint8_t)(aux[k / 4] >> (8 * (k % 4)));
   }
 
   BWTC_PROF(5);
@@ -758,6 +785,7 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
     if (p < valid) {
       keys_out[g] = kk;
       vals_out[g] = vv;
+      if (AUX) aux_out[g] = s_aux[p];
     }
   }
   BWTC_PROF(8);
@@ -787,7 +815,8 @@ struct RerankParams {
   uint32_t ctr_slot;        // ctrl word used as the dynamic tile counter of this launch
   uint32_t id_mask;         // ROUND0: the sorted payload is id | code(T[id-1]) << id_bits when packed != 0
   uint32_t id_bits;
-  uint32_t packed;
+  uint32_t packed;          // 1: predecessor code above the id; 2: predecessor codes in pred_aux[] (sorted order)
+  const uint8_t* pred_aux;
   uint8_t decode[256];      // dense code -> byte (packed emission)
   uint32_t nbuckets;        // > 1: bucketed scatter — instead of writing rank[] the tile stages its (id, rank) pairs
   uint32_t bucket_magic;    //      grouped by id bucket (bucket = min(umulhi(id, magic), nbuckets-1)); see k_scatter_bucket
@@ -905,7 +934,20 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
     }
   }
   uint32_t pc0 = 0, pc1 = 0;  // packed predecessor codes of the 8 records (one byte each)
-  if (ROUND0 && rp.packed) {
+  if (ROUND0 && rp.packed == 2u) {
+    if (tile_base + TILE <= m) {
+      const uint2 v = *reinterpret_cast<const uint2*>(rp.pred_aux + j0);  // j0 % 8 == 0, buffer 256-byte aligned
+      pc0 = v.x;
+      pc1 = v.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        const uint32_t c = (j0 + k < m) ? rp.pred_aux[j0 + k] : 0u;
+        if (k < 4) pc0 |= c << (8 * k);
+        else pc1 |= c << (8 * (k - 4));
+      }
+    }
+  } else if (ROUND0 && rp.packed) {
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       const uint32_t c = id[k] >> rp.id_bits;

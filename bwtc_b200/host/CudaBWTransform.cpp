@@ -120,12 +120,12 @@ void CudaBWTransform::doTransform(std::vector<BWTBlock*>& blocks, uint32 starts,
   bwtc_cuda_get_stats(m_ctx, &m_stats);
 }
 
-/* Unlike the reference engines (which return 0, Divsufsorter.hpp:67-70) these are real: ~35 bytes of device
+/* Unlike the reference engines (which return 0, Divsufsorter.hpp:67-70) these are real: ~37 bytes of device
  * scratch per suffix plus look-back status words. */
-uint64 CudaBWTransform::maxSizeInBytes(uint64 block_size) const { return 36 * (block_size + 1) + (1u << 20); }
+uint64 CudaBWTransform::maxSizeInBytes(uint64 block_size) const { return 38 * (block_size + 1) + (1u << 20); }
 uint64 CudaBWTransform::maxBlockSize(uint64 memory_budget) const {
   if (memory_budget <= (1u << 20) + 64) return 0;
-  uint64 b = (memory_budget - (1u << 20)) / 36 - 1;
+  uint64 b = (memory_budget - (1u << 20)) / 38 - 1;
   return b > BWTC_CUDA_MAX_BLOCK ? BWTC_CUDA_MAX_BLOCK : b;
 }
 uint64 CudaBWTransform::suggestedBlockSize(uint64 memory_budget) const {

@@ -243,6 +243,8 @@ ENGINE_KNOBS = [
     {"BWTC_RERANK_WINDOW_MB": "1", "BWTC_BUCKET_MIN_WINDOWS": "0"},  # one k_rerank launch per id window
     {"BWTC_RERANK_WINDOW_MB": "4", "BWTC_BUCKET_MIN_WINDOWS": "2"},  # bucketed scatter with exactly two buckets
     {"BWTC_PACK_PRED": "0"},                                         # BWT characters gathered from the text
+    {"BWTC_PACK_PRED": "0", "BWTC_AUX_MIN_MIB": "0"},                # predecessor codes as a one-byte payload array
+    {"BWTC_PACK_PRED": "0", "BWTC_AUX_MIN_MIB": "0", "BWTC_RERANK_WINDOW_MB": "1"},  # ... with the bucketed scatter
     {"BWTC_SEG": "0"},                                               # global radix rounds only (no segmented rounds)
     {"BWTC_SEG": "0", "BWTC_RERANK_WINDOW_MB": "1"},                 # bucketed scatter in doubling rounds too
 ]
