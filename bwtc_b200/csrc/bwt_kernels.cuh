@@ -46,6 +46,11 @@ constexpr uint32_t LB_SPIN_LIMIT = 1u << 24;
 // satisfy dt * BATCH >> RT or the walk chases an ever longer chain of aggregate-only predecessors.
 constexpr int LB_BATCH = BWTC_LB_BATCH;
 
+// Record streams of k_radix_pass: plain loads, streaming (evict-first) stores.  Measured on the 32 MiB Markov block:
+// .cs stores -1.9% sort time, .cg stores the same, .cs loads +1.6% (profiles/r01_experiments.md).
+#define BWTC_LD(p) (*(p))
+#define BWTC_ST(p, v) __stcs(p, v)
+
 #ifndef BWTC_RS_BLOCK
 #define BWTC_RS_BLOCK 256
 #endif
@@ -611,9 +616,9 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
   const uint32_t first = tile_base + warp * (32 * IPT) + lane;
   if (valid == (uint32_t)TILE) {
 #pragma unroll
-    for (int k = 0; k < IPT; ++k) key[k] = keys_in[first + 32 * k];
+    for (int k = 0; k < IPT; ++k) key[k] = BWTC_LD(keys_in + first + 32 * k);
 #pragma unroll
-    for (int k = 0; k < IPT; ++k) val[k] = IOTA ? (iota_top - (first + 32 * k)) : vals_in[first + 32 * k];
+    for (int k = 0; k < IPT; ++k) val[k] = IOTA ? (iota_top - (first + 32 * k)) : BWTC_LD(vals_in + first + 32 * k);
     if (IOTA && pack_bits) {
 #pragma unroll
       for (int k = 0; k < IPT; ++k) {
@@ -783,8 +788,8 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
     const uint32_t d = (uint32_t)(kk >> shift) & 0xFFu;
     const uint32_t g = s_binbase[d] + p;
     if (p < valid) {
-      keys_out[g] = kk;
-      vals_out[g] = vv;
+      BWTC_ST(keys_out + g, kk);
+      BWTC_ST(vals_out + g, vv);
       if (AUX) aux_out[g] = s_aux[p];
     }
   }

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""tests/gpu_variants.py — times radix-pass tile-shape variants (libbwtc_cuda_B*_I*_M*.so) on a GPU box."""
+"""tests/gpu_variants.py — parity-checks and times experiment builds of the engine (bwtc_b200/libbwtc_cuda_V*.so,
+built with __graft_entry__.build_cuda(extra_defs=[...], out_name=...)) on a GPU box."""
 import glob
 import os
 import sys
@@ -11,9 +12,9 @@ sys.path.insert(0, ROOT)
 import bwtc_b200 as bw  # noqa: E402
 
 n = int(os.environ.get("MIB", "32")) << 20
-inputs = {"markov": (9, 8), "dna": (16, 8), "random": (4, 4)}
+inputs = {"markov": (0, 0), "dna": (0, 0), "random": (0, 0)}
 data = {k: bw.generate(k, n, seed=5) for k in inputs}
-libs = sorted(glob.glob(os.path.join(ROOT, "bwtc_b200", "libbwtc_cuda_B*.so")))
+libs = sorted(glob.glob(os.path.join(ROOT, "bwtc_b200", "libbwtc_cuda_V*.so")))
 import ctypes
 orc = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
 orc.oracle_bwt_block.restype = ctypes.c_int64
