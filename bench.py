@@ -347,7 +347,9 @@ def main_gpu(args):
                            "l2": "every step streams 512 MiB of fresh blocks per GPU through ~1 GiB of scratch per "
                                  "in-flight block, far larger than the 126 MB L2 (no flush needed)",
                            "parallelism": "independent blocks sharded by rank, no collective on the data path",
-                           "host": "rank 0 bound to %s host cores (NVML affinity of its GPU)" % (bound_cpus if bound_cpus else "all")},
+                           "host": "rank 0 bound to %s host cores (NVML affinity of its GPU)" % (bound_cpus if bound_cpus else "all"),
+                           "lookback_tile_ids": "tickets (watchdog fallback)" if any(s["flags"] & 1 for s in last_stats)
+                           else "block index"},
                 "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": nb * n,
                         "d2h_bytes_per_step": nb * (n + 4 * STARTS + 256 * 4)},
                 "gpu_launches": int(ltot.item()),

@@ -59,7 +59,7 @@ class Stats(ctypes.Structure):
         ("sort0_launches", ctypes.c_uint32),
         ("sort0_bytes", ctypes.c_uint64),
         ("sort0_ms", ctypes.c_float),
-        ("reserved", ctypes.c_uint32),
+        ("flags", ctypes.c_uint32),
     ]
 
     def as_dict(self) -> dict:
@@ -72,7 +72,7 @@ class Stats(ctypes.Structure):
             "kernel_launches": int(self.kernel_launches), "algorithmic_bytes": int(self.algorithmic_bytes),
             "gpu_ms": float(self.gpu_ms), "sort_ms": float(self.sort_ms), "sort_bytes": int(self.sort_bytes),
             "sort_launches": int(self.sort_launches), "sort0_launches": int(self.sort0_launches),
-            "sort0_bytes": int(self.sort0_bytes), "sort0_ms": float(self.sort0_ms),
+            "sort0_bytes": int(self.sort0_bytes), "sort0_ms": float(self.sort0_ms), "flags": int(self.flags),
         }
 
 

@@ -84,6 +84,10 @@ struct bwtc_cuda_ctx {
   int timing_detail = 0;
   // ---- policy knobs (defaults are the measured optimum on B200; the environment variables in bwtc_cuda_ctx_create
   //      exist so that tests can force every code path, see tests/test_gpu_parity.py)
+  int static_tiles = 1;           // look-back kernels take blockIdx.x as tile id (0: dynamic tickets); cleared for good
+                                  // if the spin watchdog ever fires
+  int lb_watchdog = 0;            // the last transform failed on the look-back watchdog
+  int debug_fake_watchdog = 0;    // test hook: pretend the watchdog fired while static tile ids are in use
   int use_seg = 1;                // segmented (sort-free) doubling rounds when every group is small
   int use_batch = 1;              // small equal-sized blocks of one call are sorted as one text
   int use_pack_pred = 1;          // carry code(T[id-1]) above the id through the round-0 sort when it fits
@@ -270,11 +274,12 @@ int run_sort_impl(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first
     if (iota)
       k_radix_pass<KeyT, RS_BLOCK, IPT, true, AUX><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-          CTR_PASS0 + p, iota_top, pack_bits, topshift, pred_mask, nullptr, ctx->d_aux[cur ^ 1]);
+          ctx->static_tiles ? CTR_STATIC : (uint32_t)(CTR_PASS0 + p), iota_top, pack_bits, topshift, pred_mask, nullptr,
+          ctx->d_aux[cur ^ 1]);
     else
       k_radix_pass<KeyT, RS_BLOCK, IPT, false, AUX><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, ctx->d_idx[cur], kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-          CTR_PASS0 + p, iota_top, 0u, 0u, 0u, ctx->d_aux[cur], ctx->d_aux[cur ^ 1]);
+          ctx->static_tiles ? CTR_STATIC : (uint32_t)(CTR_PASS0 + p), iota_top, 0u, 0u, 0u, ctx->d_aux[cur], ctx->d_aux[cur ^ 1]);
     CK(ctx, cudaGetLastError());
     if (pt->end()) return BWTC_CUDA_ECUDA;
     ctx->stats.kernel_launches++;
@@ -331,7 +336,7 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
     const uint32_t win_ids = div_up(N, nwin);
     rp.win_lo = 0;
     rp.win_hi = 0xFFFFFFFFu;
-    rp.ctr_slot = CTR_RERANK;
+    rp.ctr_slot = ctx->static_tiles ? CTR_STATIC : (uint32_t)CTR_RERANK;
     rp.nbuckets = nwin;
     rp.bucket_magic = (uint32_t)(((1ull << 32) + win_ids - 1) / win_ids);
     StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, 1, ctx->d_idx[cur ^ 1], ctx->d_scat, woff};
@@ -347,7 +352,7 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
   for (uint32_t w = 0; w < nwin; ++w) {
     rp.win_lo = (uint32_t)((uint64_t)N * w / nwin);
     rp.win_hi = (w + 1 == nwin) ? 0xFFFFFFFFu : (uint32_t)((uint64_t)N * (w + 1) / nwin);
-    rp.ctr_slot = CTR_RERANK + w;
+    rp.ctr_slot = ctx->static_tiles ? CTR_STATIC : (uint32_t)(CTR_RERANK + w);
     rp.nbuckets = 0;
     rp.bucket_magic = 0;
     StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, w == 0 ? 1 : 0, nullptr, nullptr, nullptr};
@@ -375,10 +380,10 @@ constexpr int64_t BATCH_NEEDS_SINGLE = -1000;  // all 256 byte values present: n
 // The engine proper.  block_mode: in = X (n block bytes), result n bytes.  raw: in = T (n bytes), result n bytes.
 // in_dev / out_dev: device pointers supplied by the caller (or nullptr -> staged through the context).
 // bs != nullptr: batch of blocks (block contract); h_in/h_out/in_dev/out_dev/LF/nLF/freqs come from *bs.
-int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, uint8_t* h_out, const uint8_t* in_dev,
-                      uint8_t* out_dev, uint32_t n, uint32_t* LF, uint32_t nLF, uint32_t* freqs,
-                      const BatchSpec* bs = nullptr) {
+int64_t run_transform_once(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, uint8_t* h_out, const uint8_t* in_dev,
+                           uint8_t* out_dev, uint32_t n, uint32_t* LF, uint32_t nLF, uint32_t* freqs, const BatchSpec* bs) {
   ctx->err[0] = 0;
+  ctx->lb_watchdog = 0;
   if (cudaSetDevice(ctx->device) != cudaSuccess) {
     set_err(ctx->err, "cudaSetDevice(%d) failed", ctx->device);
     return BWTC_CUDA_ECUDA;
@@ -605,6 +610,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
       rp.short_thresh = pl.chars > text_end ? 0u : text_end - pl.chars + 1u;
     }
     rp.lo_bits = 0;
+    S.flags = (ctx->static_tiles ? 0u : 1u) | (bs ? 2u : 0u) | (pack_pred ? 4u : 0u) | (aux_pred ? 8u : 0u);
     rp.packed = pack_pred ? 1u : (aux_pred ? 2u : 0u);
     rp.pred_aux = ctx->d_aux[cur];
     rp.id_bits = pack_pred ? id_bits : 31u;
@@ -620,8 +626,9 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
   }
   CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_WORDS * 4, cudaMemcpyDeviceToHost, st));
   CK(ctx, cudaStreamSynchronize(st));
-  if (ctx->h_ctrl()[CTR_ERR]) {
+  if (ctx->h_ctrl()[CTR_ERR] || (ctx->debug_fake_watchdog && ctx->static_tiles)) {
     set_err(ctx->err, "look-back watchdog fired in round 0 (code %u)", ctx->h_ctrl()[CTR_ERR]);
+    ctx->lb_watchdog = 1;
     return BWTC_CUDA_EINTERNAL;
   }
   uint32_t live = ctx->h_ctrl()[CTR_LIVE];
@@ -766,6 +773,7 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     CK(ctx, cudaStreamSynchronize(st));
     if (ctx->h_ctrl()[CTR_ERR]) {
       set_err(ctx->err, "look-back watchdog fired in round %u (code %u)", r, ctx->h_ctrl()[CTR_ERR]);
+      ctx->lb_watchdog = 1;
       return BWTC_CUDA_EINTERNAL;
     }
     if (!from_list && ctx->h_ctrl()[CTR_CURSOR] != m) {
@@ -835,6 +843,39 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     S.sort0_ms = tot0;
   }
   return (int64_t)LF[0];
+}
+
+// run_transform_once + the fallback of the static tile ids (see k_radix_pass): if the look-back watchdog fired, the
+// context switches to ticket counters for good and — when the caller's input is still intact — repeats the call.
+int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, uint8_t* h_out, const uint8_t* in_dev,
+                      uint8_t* out_dev, uint32_t n, uint32_t* LF, uint32_t nLF, uint32_t* freqs,
+                      const BatchSpec* bs = nullptr) {
+  // freqs are incremented before any look-back kernel runs: hand the first attempt a scratch copy
+  std::vector<uint32_t> fr_tmp;
+  uint32_t* fr = freqs;
+  BatchSpec b2;
+  if (freqs && ctx->static_tiles) {
+    fr_tmp.assign((size_t)256 * (bs ? bs->nblocks : 1u), 0u);
+    fr = fr_tmp.data();
+    if (bs) { b2 = *bs; b2.freqs = fr; }
+  }
+  const bool scratch = (fr != freqs);
+  int64_t rc = run_transform_once(ctx, block_mode, h_in, h_out, in_dev, out_dev, n, LF, nLF, fr, (bs && scratch) ? &b2 : bs);
+  if (rc == BWTC_CUDA_EINTERNAL && ctx->lb_watchdog && ctx->static_tiles) {
+    ctx->static_tiles = 0;
+    bool intact = bs ? !bs->on_device : (in_dev == nullptr || in_dev != out_dev);
+    if (bs && bs->on_device) {
+      intact = true;
+      for (uint32_t k = 0; k < bs->nblocks; ++k) intact = intact && (bs->in[k] != bs->out[k]);
+    }
+    if (intact) {
+      if (scratch) std::fill(fr_tmp.begin(), fr_tmp.end(), 0u);
+      rc = run_transform_once(ctx, block_mode, h_in, h_out, in_dev, out_dev, n, LF, nLF, fr, (bs && scratch) ? &b2 : bs);
+    }
+  }
+  if (scratch && rc >= 0)
+    for (size_t i = 0; i < fr_tmp.size(); ++i) freqs[i] += fr_tmp[i];
+  return rc;
 }
 
 // count blocks (block contract) through one context: as ONE batch when they qualify — 2..MAX_BATCH blocks, all of
@@ -929,6 +970,8 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (!c) { set_err(g_err, "out of host memory"); return BWTC_CUDA_EALLOC; }
   c->device = device;
   c->cap = max_block_bytes;
+  if (const char* e = getenv("BWTC_STATIC_TILES")) c->static_tiles = atoi(e);
+  if (const char* e = getenv("BWTC_DEBUG_FAKE_WATCHDOG")) c->debug_fake_watchdog = atoi(e);
   if (const char* e = getenv("BWTC_SEG")) c->use_seg = atoi(e);
   if (const char* e = getenv("BWTC_BATCH")) c->use_batch = atoi(e);
   if (const char* e = getenv("BWTC_PACK_PRED")) c->use_pack_pred = atoi(e);

@@ -26,6 +26,7 @@ constexpr uint32_t RANK_MASK = 0x7FFFFFFFu;
 
 // ---- control words (one uint32 array per context, zeroed by a memset at the start of every round)
 constexpr int CTR_PASS0 = 0;       // [0..15]  dynamic tile counters of the radix passes of this round
+constexpr uint32_t CTR_STATIC = 0xFFFFFFFFu;  // "no ticket counter: tile id = blockIdx.x"
 constexpr int CTR_RERANK = 32;     // [32..47] dynamic tile counters of the k_rerank window launches
 constexpr int MAX_RERANK_WINDOWS = 16;
 constexpr int CTR_CURSOR = 17;     // output cursor of k_build_keys (== number of live records emitted)
@@ -595,10 +596,15 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
 #ifdef BWTC_PROFILE_STAGES
   const unsigned long long t_entry = clock64();
 #endif
-  if (tid == 0) s_misc[0] = atomicAdd(&ctrl[ctr_slot], 1u);
+  // Tile id.  ctr_slot == CTR_STATIC: the block index — CTAs of a 1-D grid are dispatched in index order, so every
+  // tile a CTA can wait for (lower ids only) is already resident or finished; measured 4-7% faster than taking a
+  // ticket (no atomic + broadcast in front of the loads).  The order is not an architectural guarantee: the spin
+  // watchdog turns a violation into an error, and the host then repeats the block with tickets (ctr_slot = a
+  // zeroed ctrl word), which are safe under any dispatch order.
+  if (ctr_slot != CTR_STATIC && tid == 0) s_misc[0] = atomicAdd(&ctrl[ctr_slot], 1u);
   for (int i = tid; i < WARPS * 256; i += BLOCK) s_whist[i] = 0;
   __syncthreads();
-  const uint32_t tile = s_misc[0];
+  const uint32_t tile = (ctr_slot != CTR_STATIC) ? s_misc[0] : blockIdx.x;
 #ifdef BWTC_PROFILE_STAGES
   if (tid == 0 && g_prof_buf) g_prof_buf[(size_t)tile * 16 + 0] = t_entry;
 #endif
@@ -894,7 +900,7 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
   __shared__ uint8_t s_dec[ROUND0 ? 256 : 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    s_tile = atomicAdd(&ctrl[rp.ctr_slot], 1u);
+    s_tile = (rp.ctr_slot != CTR_STATIC) ? atomicAdd(&ctrl[rp.ctr_slot], 1u) : blockIdx.x;  // see k_radix_pass
   }
   if (ROUND0 && rp.packed) s_dec[tid] = rp.decode[tid];
   if (tid <= MAX_RERANK_WINDOWS) s_bcnt[tid] = 0;

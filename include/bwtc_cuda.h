@@ -64,7 +64,9 @@ typedef struct bwtc_cuda_stats {
   uint32_t sort0_launches;                  /* ... of which round-0 passes (all N records each) */
   uint64_t sort0_bytes;                     /* algorithmic bytes moved by the round-0 passes */
   float    sort0_ms;                        /* device time inside the round-0 passes (detailed timing on) */
-  uint32_t reserved;
+  uint32_t flags;            /* bit 0: look-back kernels ran with ticket counters (watchdog fallback or BWTC_STATIC_TILES=0);
+                              * bit 1: the blocks of a batch were sorted as one text; bit 2: predecessor codes packed above the ids;
+                              * bit 3: ... carried as a one-byte payload array */
 } bwtc_cuda_stats;
 
 /* ---- library / device ------------------------------------------------------------------------ */

@@ -245,6 +245,8 @@ ENGINE_KNOBS = [
     {"BWTC_PACK_PRED": "0"},                                         # BWT characters gathered from the text
     {"BWTC_PACK_PRED": "0", "BWTC_AUX_MIN_MIB": "0"},                # predecessor codes as a one-byte payload array
     {"BWTC_PACK_PRED": "0", "BWTC_AUX_MIN_MIB": "0", "BWTC_RERANK_WINDOW_MB": "1"},  # ... with the bucketed scatter
+    {"BWTC_STATIC_TILES": "0"},                                      # look-back kernels take tile tickets
+    {"BWTC_DEBUG_FAKE_WATCHDOG": "1"},                               # watchdog fallback: retry with tickets
     {"BWTC_SEG": "0"},                                               # global radix rounds only (no segmented rounds)
     {"BWTC_SEG": "0", "BWTC_RERANK_WINDOW_MB": "1"},                 # bucketed scatter in doubling rounds too
 ]
@@ -271,6 +273,11 @@ def test_every_engine_path_is_bit_exact(oracle, monkeypatch, knobs):
             assert (got[0] == want[0]).all(), (kind, knobs)
             assert (got[1] == want[1]).all(), (kind, knobs)
             assert (got[2] == want[2]).all(), (kind, knobs)
+        flags = ctx.stats()["flags"]
+        if knobs.get("BWTC_STATIC_TILES") == "0" or knobs.get("BWTC_DEBUG_FAKE_WATCHDOG") == "1":
+            assert flags & 1, "the look-back kernels should have run with ticket counters"
+        else:
+            assert not (flags & 1), "unexpected watchdog fallback"
     finally:
         ctx.close()
 
