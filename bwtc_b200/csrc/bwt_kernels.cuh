@@ -601,10 +601,14 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
   // ticket (no atomic + broadcast in front of the loads).  The order is not an architectural guarantee: the spin
   // watchdog turns a violation into an error, and the host then repeats the block with tickets (ctr_slot = a
   // zeroed ctrl word), which are safe under any dispatch order.
-  if (ctr_slot != CTR_STATIC && tid == 0) s_misc[0] = atomicAdd(&ctrl[ctr_slot], 1u);
-  for (int i = tid; i < WARPS * 256; i += BLOCK) s_whist[i] = 0;
-  __syncthreads();
-  const uint32_t tile = (ctr_slot != CTR_STATIC) ? s_misc[0] : blockIdx.x;
+  uint32_t tile = blockIdx.x;
+  if (ctr_slot != CTR_STATIC) {
+    if (tid == 0) s_misc[0] = atomicAdd(&ctrl[ctr_slot], 1u);
+    __syncthreads();
+    tile = s_misc[0];
+  }
+  // (the per-warp histograms are zeroed AFTER the loads have been issued: their latency covers the zeroing and
+  // the barrier)
 #ifdef BWTC_PROFILE_STAGES
   if (tid == 0 && g_prof_buf) g_prof_buf[(size_t)tile * 16 + 0] = t_entry;
 #endif
@@ -659,6 +663,8 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
     }
   }
 
+  for (int i = lane; i < 256; i += 32) s_whist[warp * 256 + i] = 0;  // each warp zeroes (and then ranks into) its own
+  __syncwarp();
 #ifdef BWTC_PROFILE_STAGES
   {
     KeyT acc = 0;
@@ -899,13 +905,16 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
   __shared__ uint32_t s_bcnt[MAX_RERANK_WINDOWS + 1];
   __shared__ uint8_t s_dec[ROUND0 ? 256 : 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    s_tile = (rp.ctr_slot != CTR_STATIC) ? atomicAdd(&ctrl[rp.ctr_slot], 1u) : blockIdx.x;  // see k_radix_pass
-  }
+  // tile id: the block index, or a ticket in the watchdog-fallback mode (see k_radix_pass).  s_bcnt / s_dec are first
+  // read behind later barriers, so the block-index path needs no barrier in front of the loads.
+  uint32_t tile = blockIdx.x;
   if (ROUND0 && rp.packed) s_dec[tid] = rp.decode[tid];
   if (tid <= MAX_RERANK_WINDOWS) s_bcnt[tid] = 0;
-  __syncthreads();
-  const uint32_t tile = s_tile;
+  if (rp.ctr_slot != CTR_STATIC) {
+    if (tid == 0) s_tile = atomicAdd(&ctrl[rp.ctr_slot], 1u);
+    __syncthreads();
+    tile = s_tile;
+  }
   const uint32_t m = rp.m;
   const uint32_t tile_base = tile * (uint32_t)TILE;
   if (tile_base >= m) return;
