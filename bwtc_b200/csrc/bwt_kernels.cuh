@@ -3,13 +3,18 @@
 // Algorithm: suffix array by prefix doubling, never materialised as an array —
 // the engine keeps the inverse suffix array rank[] (ISA) and refines it:
 //   round 0   : key(i) = first c characters of suffix i as dense b-bit codes (k_pack_round0),
-//               LSD radix sort of (key, suffix id) with one-sweep digit passes (k_radix_pass),
-//               segmented re-rank (k_rerank<ROUND0>): rank[i] = index of i's group head, singletons
-//               flagged RANK_DONE.
-//   round r>0 : text-order scan of rank[] emits a packed (rank[i], rank[i+h]) 64-bit key for every
-//               still-live suffix (k_build_keys, compaction fused), same radix sort, k_rerank<false>.
-//   final     : out[rank[i]] = T[i-1] fused with pidx / LFpowers extraction and the bwtc hole-fill
-//               (k_final).
+//               LSD radix sort of (key, suffix id [, predecessor code]) with one-sweep digit passes
+//               (k_radix_pass), segmented re-rank (k_rerank<ROUND0>): rank[i] = index of i's group head,
+//               singletons flagged RANK_DONE and their BWT byte emitted at once.
+//   round r>0 : (a) at most 2048 suffixes live: one CTA finishes everything (k_small_rounds);
+//               (b) every group <= 128 suffixes: groups are ordered in shared memory without a global sort
+//                   (k_seg_round + k_apply_ranks) from the rank-ordered live lists k_rerank staged;
+//               (c) otherwise a packed (rank[i] >> 1, rank[i+h] + 1) 64-bit key for every still-live suffix
+//                   (k_build_keys in text order, or k_build_from_list), same radix sort, k_rerank<false>.
+//   final     : pidx / LFpowers extraction and the bwtc hole-fill (k_finish); the BWT bytes were written by the
+//               re-rank kernels (emit_bwt) the moment each suffix became unique.
+//   batches   : runs of small equal-sized blocks are one text with the block number on top of every key and a
+//               reserved sentinel code (k_prep_batch, k_finish_batch).
 // All of this replaces sort_typeBstar + sssort + trsort + construct_BWT of the reference
 // (bwtransforms/divsufsort.c:38-192,328-404; sssort.c:746-815; trsort.c:554-586) — it is NOT a port of
 // them: no B*-suffix classification, no induced sorting, no introsort.
@@ -25,9 +30,9 @@ constexpr uint32_t RANK_DONE = 0x80000000u;  // bit 31 of rank[i]: suffix i is a
 constexpr uint32_t RANK_MASK = 0x7FFFFFFFu;
 
 // ---- control words (one uint32 array per context, zeroed by a memset at the start of every round)
-constexpr int CTR_PASS0 = 0;       // [0..15]  dynamic tile counters of the radix passes of this round
+constexpr int CTR_PASS0 = 0;       // [0..15]  tile ticket counters of the radix passes (watchdog-fallback mode only)
 constexpr uint32_t CTR_STATIC = 0xFFFFFFFFu;  // "no ticket counter: tile id = blockIdx.x"
-constexpr int CTR_RERANK = 32;     // [32..47] dynamic tile counters of the k_rerank window launches
+constexpr int CTR_RERANK = 32;     // [32..47] tile ticket counters of the k_rerank window launches (fallback mode only)
 constexpr int MAX_RERANK_WINDOWS = 16;
 constexpr int CTR_CURSOR = 17;     // output cursor of k_build_keys (== number of live records emitted)
 constexpr int CTR_LIVE = 18;       // records still in non-singleton groups after k_rerank
@@ -816,9 +821,9 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
 //   HF(j), HH(j) = position of the last headfull / headhi at or before j  (two max-scans: thread-local,
 //                  warp shuffles, CTA, and a single 64-bit decoupled look-back word across tiles);
 //   new rank   = old_rank + HF(j) - HH(j)   (ROUND0: HF(j));   singleton = headfull(j) && headfull(j+1).
-// rank[idx[j]] is scattered only when it changes or becomes final.  The count of records left in
-// non-singleton groups goes to ctrl[CTR_LIVE]; no compacted list is written — k_build_keys re-derives
-// liveness from the RANK_DONE bit in text order.
+// rank[idx[j]] is scattered only when it changes or becomes final (directly, per id window, or staged per id
+// bucket for k_scatter_bucket).  Records left in non-singleton groups are staged in sorted order per tile
+// (StageParams) and counted in ctrl[CTR_LIVE]; the largest group goes to ctrl[CTR_MAXGROUP].
 // Replaces the rank assignment of sort_typeBstar (divsufsort.c:147-158) and tr_partition / tr_copy
 // bookkeeping (trsort.c:220-323), negative-run skipping (trsort.c:563-585).
 // =====================================================================================================
