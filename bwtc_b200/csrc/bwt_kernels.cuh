@@ -541,13 +541,14 @@ __global__ void __launch_bounds__(256) k_build_keys(const uint32_t* __restrict__
 
 // =====================================================================================================
 // k_radix_pass — one 8-bit digit pass of the LSD radix sort over (key, suffix id) records, single sweep:
-//   * dynamic tile ids (atomic ticket) so a tile only ever waits on tiles that already started,
+//   * tile id = block index (CTAs are dispatched in index order, so a tile only ever waits on tiles that already
+//     started); atomic tickets only in the watchdog-fallback mode,
 //   * warp-striped coalesced loads, keys/values held in registers,
 //   * per-warp digit ranking with 8 ballots per item (match_digit8) into per-warp shared histograms,
 //   * per-digit decoupled look-back across tiles (status word = 2 flag bits + 30-bit count; the data
 //     travels inside the flag word, so no fence is needed), with a spin watchdog instead of a hang,
 //   * records are staged in shared memory in sorted order and written out with consecutive threads
-//     writing consecutive addresses of a bin's run (coalesced scatter).
+//     writing consecutive addresses of a bin's run (coalesced scatter, streaming stores).
 // HBM traffic per record: read key+id, write key+id — the algorithmic minimum for an out-of-place pass.
 // IOTA: first pass of round 0 — suffix ids are implied by position (id = iota_top - position), not read.
 // Stable, which the round-0 sentinel handling relies on.
@@ -834,7 +835,7 @@ struct RerankParams {
   uint32_t win_lo, win_hi;  // only suffix ids in [win_lo, win_hi) are written / counted by this launch: the rank
                             // scatter of a big block is split into windows that stay L2-resident (random 4-byte
                             // writes into a >L2 array cost a DRAM sector fill + write-back each)
-  uint32_t ctr_slot;        // ctrl word used as the dynamic tile counter of this launch
+  uint32_t ctr_slot;        // CTR_STATIC (tile id = block index) or the ctrl word used as tile ticket counter
   uint32_t id_mask;         // ROUND0: the sorted payload is id | code(T[id-1]) << id_bits when packed != 0
   uint32_t id_bits;
   uint32_t packed;          // 1: predecessor code above the id; 2: predecessor codes in pred_aux[] (sorted order)
@@ -1305,8 +1306,8 @@ __global__ void __launch_bounds__(256) k_gather_chunks(const uint32_t* __restric
 }
 
 // =====================================================================================================
-// k_build_from_list — doubling-round key build for rounds with few live suffixes: the ids come from the list
-// k_rerank appended (no scan over all N ranks); two rank gathers per record.  Same key layout and fused
+// k_build_from_list — doubling-round key build for rounds with few live suffixes: the ids come from the compact
+// list built from k_rerank's staging (no scan over all N ranks); two rank gathers per record.  Same key layout and fused
 // histograms as k_build_keys.
 // =====================================================================================================
 __global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restrict__ list, uint32_t m,
