@@ -1347,9 +1347,12 @@ __global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restr
 // block's second round).  Input may contain holes (RANK_DONE records of the previous global sort).
 // Replaces tr_introsort over small groups (trsort.c:327-552).
 // =====================================================================================================
+#ifndef BWTC_SEG_MINB
+#define BWTC_SEG_MINB 4
+#endif
 constexpr int SEG_T = 1920, SEG_CAP = 2048, SEG_MAXGROUP = 128;
 
-__global__ void __launch_bounds__(256) k_seg_round(const uint32_t* __restrict__ nr_in, const uint32_t* __restrict__ id_in,
+__global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const uint32_t* __restrict__ nr_in, const uint32_t* __restrict__ id_in,
                                                    uint32_t m_in, const uint32_t* __restrict__ rank, uint32_t N,
                                                    uint32_t h, EmitParams ep, uint32_t* __restrict__ nr_out,
                                                    uint32_t* __restrict__ id_out, uint32_t* __restrict__ upd_id,
