@@ -306,6 +306,14 @@ def main_gpu(args):
                 for _ in range(3):
                     sp.run_ptrs(sp_in, sp_out, [sn] * sb, STARTS, on_device=True, want_stats=False)
                 sms = sp.timing_end()
+                # the batched device-pointer path must agree with the host-pointer path on the same blocks
+                sh_in = [host_in[j // 32][(j % 32) * sn:(j % 32 + 1) * sn] for j in range(sb)]
+                sh_out = torch.empty(sb * sn, dtype=torch.uint8).pin_memory()
+                LFd, nLFd, frd, _ = sp.run_ptrs(sp_in, sp_out, [sn] * sb, STARTS, on_device=True, want_stats=False)
+                LFs, nLFs, frs, _ = sp.run_ptrs([t.data_ptr() for t in sh_in], [sh_out[j * sn:(j + 1) * sn].data_ptr() for j in range(sb)],
+                                                [sn] * sb, STARTS, on_device=False, want_stats=False)
+                assert (LFd == LFs).all() and (nLFd == nLFs).all() and (frd == frs).all()
+                assert torch.equal(torch.cat([t.cpu() for t in s_out]), sh_out)
                 sp.close()
                 small = {"workload": "64 x 1 MiB Markov blocks per step (BASELINE configs[0] block size), device-resident, "
                                      "pipeline depth 3, batched 32 blocks per sort", "value": 3 * sb * sn / 1e6 / (sms / 1e3),
