@@ -67,7 +67,8 @@ struct bwtc_cuda_ctx {
   uint8_t* d_aux[2] = {nullptr, nullptr};    // ping-pong one-byte payload of the round-0 sort (predecessor codes), N each
   uint32_t* d_scat = nullptr;     // u32[N]: staged ranks of the bucketed scatter (the ids go to the idle id buffer)
   uint32_t* d_zero = nullptr;     // [ctrl CTR_WORDS][hist HIST_WORDS][tstate rows of max_aux_tiles] zeroed per round
-  uint32_t* d_status = nullptr;   // [MAX_PASSES][max_rs_tiles][256] radix look-back words
+  uint32_t* d_status = nullptr;   // [MAX_PASSES][LB_PAD_ROWS + max_rs_tiles][256] radix look-back words; the pad rows in
+                                  // front of every pass hold "prefix 0" for ever, so a walk needs no bounds check
   uint32_t* d_tilecnt = nullptr;  // [2][max_aux_tiles]: per-tile live counts of k_rerank and their exclusive prefix,
                                   // then [max_aux_tiles][MAX_RERANK_WINDOWS+1] bucket offsets of the bucketed scatter
   uint32_t* d_LF = nullptr;       // [LF_PARK) LFpowers (one row of 256 per block of a batch), [LF_PARK + k] parked hole byte
@@ -269,7 +270,7 @@ int run_sort_impl(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first
     if (!((pass_mask >> p) & 1u)) continue;
     const KeyT* kin = static_cast<const KeyT*>(ctx->d_keys[cur]);
     KeyT* kout = static_cast<KeyT*>(ctx->d_keys[cur ^ 1]);
-    uint32_t* status = ctx->d_status + (size_t)p * ctx->max_rs_tiles * 256u;
+    uint32_t* status = ctx->d_status + ((size_t)p * (ctx->max_rs_tiles + LB_PAD_ROWS) + LB_PAD_ROWS) * 256u;
     if (pt->begin()) return BWTC_CUDA_ECUDA;
     if (iota)
       k_radix_pass<KeyT, RS_BLOCK, IPT, true, AUX><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
@@ -316,7 +317,8 @@ int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m, uint32_t rs_til
   const uint32_t tiles = div_up(m, rs_tile);
   for (int p = 0; p < MAX_PASSES; ++p)
     if ((pass_mask >> p) & 1u)
-      CK(ctx, cudaMemsetAsync(ctx->d_status + (size_t)p * ctx->max_rs_tiles * 256u, 0, (size_t)tiles * 1024u, ctx->stream));
+      CK(ctx, cudaMemsetAsync(ctx->d_status + ((size_t)p * (ctx->max_rs_tiles + LB_PAD_ROWS) + LB_PAD_ROWS) * 256u, 0,
+                              (size_t)tiles * 1024u, ctx->stream));
   return 0;
 }
 
@@ -1009,7 +1011,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_idx[0], N * 4);
   ALLOC(c->d_idx[1], N * 4);
   ALLOC(c->d_zero, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)MAX_RERANK_WINDOWS * c->max_aux_tiles * 8 + 64);
-  ALLOC(c->d_status, (size_t)MAX_PASSES * c->max_rs_tiles * 1024u);
+  ALLOC(c->d_status, (size_t)MAX_PASSES * (c->max_rs_tiles + LB_PAD_ROWS) * 1024u);
   ALLOC(c->d_LF, (size_t)LF_WORDS * 4);
   ALLOC(c->d_bhist, (size_t)MAX_BATCH * 256 * 4);
   ALLOC(c->d_bptr, (size_t)MAX_BATCH * sizeof(void*));
@@ -1019,6 +1021,14 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_aux[0], padded);
   ALLOC(c->d_aux[1], padded);
 #undef ALLOC
+  if (!rc) {  // pad rows of the look-back status: "inclusive prefix = 0", never overwritten
+    std::vector<uint32_t> pad((size_t)LB_PAD_ROWS * 256, LB_PREFIX);
+    for (int p = 0; p < MAX_PASSES && !rc; ++p) {
+      e = cudaMemcpy(c->d_status + (size_t)p * (c->max_rs_tiles + LB_PAD_ROWS) * 256u, pad.data(), pad.size() * 4,
+                     cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { set_err(g_err, "cudaMemcpy(status pad): %s", cudaGetErrorString(e)); rc = BWTC_CUDA_ECUDA; }
+    }
+  }
   if (!rc) {
     e = cudaMallocHost((void**)&c->h_small, (size_t)(CTR_WORDS + HIST_WORDS + 256 + 8) * 4);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_batch, (size_t)MAX_BATCH * (sizeof(void*) + 2 * 256 * 4));

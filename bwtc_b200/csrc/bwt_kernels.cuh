@@ -44,6 +44,7 @@ constexpr int CTR_WORDS = 64;
 // look-back status words of the radix pass: 2 flag bits + 30-bit count
 constexpr uint32_t LB_AGG = 0x40000000u, LB_PREFIX = 0x80000000u, LB_VALUE = 0x3FFFFFFFu;
 constexpr uint32_t LB_SPIN_LIMIT = 1u << 24;
+constexpr int LB_PAD_ROWS = 8;  // rows of "prefix 0" in front of tile 0 (>= LB_BATCH): look-back loads need no bounds check
 #ifndef BWTC_LB_BATCH
 #define BWTC_LB_BATCH 8
 #endif
@@ -51,6 +52,7 @@ constexpr uint32_t LB_SPIN_LIMIT = 1u << 24;
 // and a round trip of RT cycles the look-back settles at L = RT / (1 - RT / (dt * BATCH)): the batch must
 // satisfy dt * BATCH >> RT or the walk chases an ever longer chain of aggregate-only predecessors.
 constexpr int LB_BATCH = BWTC_LB_BATCH;
+static_assert(LB_BATCH <= LB_PAD_ROWS, "the look-back batch must not read past the pad rows");
 
 // Record streams of k_radix_pass: plain loads, streaming (evict-first) stores.  Measured on the 32 MiB Markov block:
 // .cs stores -1.9% sort time, .cg stores the same, .cs loads +1.6% (profiles/r01_experiments.md).
@@ -751,28 +753,22 @@ __global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* 
         ++prof_iters;
 #endif
         uint32_t v[LB_BATCH];
+        const uint32_t* row = status + (long long)t * 256 + tid;  // rows t, t-1, ...; rows -1..-LB_PAD_ROWS are "prefix 0"
 #pragma unroll
-        for (int i = 0; i < LB_BATCH; ++i) {
-          const long long ti = t - i;
-          v[i] = (ti >= 0) ? ld_relaxed_u32(status + (size_t)ti * 256u + tid) : LB_PREFIX;
-        }
+        for (int i = 0; i < LB_BATCH; ++i) v[i] = ld_relaxed_u32(row - i * 256);
+        // branch-free walk: `alive` is all-ones while every word so far was an aggregate
+        uint32_t alive = 0xFFFFFFFFu, fin = 0;
         int consumed = 0;
-        bool stop = false;
 #pragma unroll
         for (int i = 0; i < LB_BATCH; ++i) {
-          if (!stop) {
-            if (v[i] & LB_PREFIX) {
-              excl += v[i] & LB_VALUE;
-              done = true;
-              stop = true;
-            } else if (v[i] & LB_AGG) {
-              excl += v[i] & LB_VALUE;
-              ++consumed;
-            } else {
-              stop = true;
-            }
-          }
+          const uint32_t isagg = (uint32_t)((int32_t)(v[i] << 1) >> 31);  // bit 30 -> 0 / ~0
+          const uint32_t ispre = (uint32_t)((int32_t)v[i] >> 31);         // bit 31 -> 0 / ~0
+          excl += v[i] & LB_VALUE & alive & (isagg | ispre);
+          fin |= alive & ispre;
+          consumed += (int)(alive & isagg & 1u);
+          alive &= isagg;
         }
+        done = fin != 0;
         t -= consumed;
         if (!done && consumed == 0) {
           if (++spins > LB_SPIN_LIMIT) {
