@@ -65,6 +65,9 @@ static_assert(LB_BATCH <= LB_PAD_ROWS, "the look-back batch must not read past t
 #ifndef BWTC_RS_MINB
 #define BWTC_RS_MINB 3
 #endif
+#ifndef BWTC_RS_MINB32
+#define BWTC_RS_MINB32 4
+#endif
 #ifndef BWTC_RS_IPT64
 #define BWTC_RS_IPT64 16
 #endif
@@ -575,7 +578,7 @@ struct RadixPassSmem {
 // suffix, for blocks whose id has no spare bits for it (pack_bits) and whose text is too large for an L2-resident
 // gather at emission time.  The IOTA pass produces it (top character of the next key), later passes carry it.
 template <typename KeyT, int BLOCK, int IPT, bool IOTA, bool AUX = false>
-__global__ void __launch_bounds__(BLOCK, BWTC_RS_MINB) k_radix_pass(const KeyT* __restrict__ keys_in,
+__global__ void __launch_bounds__(BLOCK, (sizeof(KeyT) == 4 && !AUX) ? BWTC_RS_MINB32 : BWTC_RS_MINB) k_radix_pass(const KeyT* __restrict__ keys_in,
                                                       const uint32_t* __restrict__ vals_in,
                                                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                       uint32_t n, uint32_t shift,
