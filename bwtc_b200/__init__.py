@@ -22,9 +22,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbwtc_cuda.so")
 GEN_LIB_PATH = os.path.join(_HERE, "libbwtc_gen.so")
-HOST_LIB_PATH = os.path.join(_HERE, "libbwtc_host.so")
+INTEGRATION_LIB_PATH = os.path.join(_HERE, "libbwtc_integration.so")
 
 MAX_ROUNDS = 40
+MAX_BLOCK = 0x3FFFFFF0            # BWTC_CUDA_MAX_BLOCK
+SCRATCH_BYTES_PER_SUFFIX = 40     # BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX
 
 
 class BwtcCudaUnavailable(RuntimeError):
@@ -60,6 +62,7 @@ class Stats(ctypes.Structure):
         ("sort0_bytes", ctypes.c_uint64),
         ("sort0_ms", ctypes.c_float),
         ("flags", ctypes.c_uint32),
+        ("batch_blocks", ctypes.c_uint32),
     ]
 
     def as_dict(self) -> dict:
@@ -73,6 +76,7 @@ class Stats(ctypes.Structure):
             "gpu_ms": float(self.gpu_ms), "sort_ms": float(self.sort_ms), "sort_bytes": int(self.sort_bytes),
             "sort_launches": int(self.sort_launches), "sort0_launches": int(self.sort0_launches),
             "sort0_bytes": int(self.sort0_bytes), "sort0_ms": float(self.sort0_ms), "flags": int(self.flags),
+            "batch_blocks": int(self.batch_blocks),
         }
 
 
@@ -88,6 +92,7 @@ C_ABI = [
     ("bwtc_cuda_global_error", ctypes.c_char_p, []),
     ("bwtc_cuda_ctx_create", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_uint32]),
     ("bwtc_cuda_ctx_destroy", None, [_vp]),
+    ("bwtc_cuda_scratch_bytes", ctypes.c_uint64, [ctypes.c_uint32]),
     ("bwtc_cuda_last_error", ctypes.c_char_p, [_vp]),
     ("bwtc_cuda_get_stats", ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
     ("bwtc_cuda_ctx_set_round0", ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32]),
@@ -108,6 +113,9 @@ C_ABI = [
     ("bwtc_cuda_pipeline_set_timing", ctypes.c_int, [_vp, ctypes.c_int]),
     ("bwtc_cuda_pipeline_run", ctypes.c_int,
      [_vp, _vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    ("bwtc_cuda_pipeline_submit", ctypes.c_int,
+     [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_uint64)]),
+    ("bwtc_cuda_pipeline_wait", ctypes.c_int, [_vp, ctypes.c_uint64]),
     ("bwtc_cuda_pipeline_timing_begin", ctypes.c_int, [_vp]),
     ("bwtc_cuda_pipeline_timing_end", ctypes.c_float, [_vp]),
 ]
@@ -267,6 +275,7 @@ class CudaBWTransform:
     levels as the reference (bwtransforms/BWTransform.hpp:53-61)."""
 
     def __init__(self, max_block_bytes: int = 1 << 20, device: int = 0):
+        self._device = device
         self._ctx = CudaContext(max_block_bytes, device)
 
     @property
@@ -275,9 +284,9 @@ class CudaBWTransform:
 
     def _ensure(self, n: int):
         if n > self._ctx.max_block_bytes:
-            dev_ctx = CudaContext(max(n, 2 * self._ctx.max_block_bytes))
-            self._ctx.close()
-            self._ctx = dev_ctx
+            want = max(n, 2 * self._ctx.max_block_bytes)
+            self._ctx.close()  # release the old scratch first: peak device memory stays one context
+            self._ctx = CudaContext(want, self._device)
 
     # raw virtual: doTransform(byte* begin, uint32 length, vector<uint32>& LF[, freqs])
     def doTransformRaw(self, begin: np.ndarray, LFpowers: np.ndarray, freqs: Optional[np.ndarray] = None) -> int:
@@ -293,10 +302,14 @@ class CudaBWTransform:
 
     # sizing hooks of BWTransform (return 0 in both reference engines, Divsufsorter.hpp:67-70); here real
     def maxSizeInBytes(self, block_size: int) -> int:
-        return 31 * (block_size + 1) + (1 << 20)
+        """Exact device scratch of a context for blocks of this size (bwtc_cuda_scratch_bytes)."""
+        return int(load_library().bwtc_cuda_scratch_bytes(block_size))
 
     def maxBlockSize(self, memory_budget: int) -> int:
-        return max(0, (memory_budget - (1 << 20)) // 31 - 1)
+        """Largest block whose scratch fits the budget (BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX = 40 is an upper bound from
+        1 MiB on; the fixed part is ~3 MiB)."""
+        b = max(0, (memory_budget - (3 << 20)) // SCRATCH_BYTES_PER_SUFFIX - 1)
+        return min(b, MAX_BLOCK)
 
     def suggestedBlockSize(self, memory_budget: int) -> int:
         return min(self.maxBlockSize(memory_budget), 32 << 20)
@@ -379,6 +392,24 @@ class Pipeline:
         if rc < 0:
             raise BwtcCudaError(rc, self._lib.bwtc_cuda_pipeline_error(self._h).decode())
         return LF, nLF, freqs, ([s.as_dict() for s in stats] if stats is not None else None)
+
+    def submit(self, block: np.ndarray, starts: int = 8, want_freqs: bool = True):
+        """Streaming form (bwtc_cuda_pipeline_submit): queues one host block for an in-place transform and returns a
+        handle; call wait(handle) to get (LFpowers, freqs).  The block must stay alive until then."""
+        h = {"block": block, "LF": np.zeros(256, np.uint32), "nLF": ctypes.c_uint32(0),
+             "freqs": np.zeros(256, np.uint32) if want_freqs else None, "ticket": ctypes.c_uint64(0)}
+        rc = self._lib.bwtc_cuda_pipeline_submit(self._h, block.ctypes.data, block.ctypes.data, block.size, starts, 0,
+                                                 h["LF"].ctypes.data, ctypes.addressof(h["nLF"]), _ptr(h["freqs"]), None,
+                                                 ctypes.byref(h["ticket"]))
+        if rc < 0:
+            raise BwtcCudaError(rc, self._lib.bwtc_cuda_pipeline_error(self._h).decode())
+        return h
+
+    def wait(self, h):
+        rc = self._lib.bwtc_cuda_pipeline_wait(self._h, h["ticket"])
+        if rc < 0:
+            raise BwtcCudaError(rc, self._lib.bwtc_cuda_pipeline_error(self._h).decode())
+        return h["LF"][: h["nLF"].value].copy(), h["freqs"]
 
     def run(self, blocks: Sequence[np.ndarray], starts: int = 8):
         """Transforms host blocks in place."""

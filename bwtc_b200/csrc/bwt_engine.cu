@@ -7,13 +7,18 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 using namespace bwtc_b200;
@@ -49,12 +54,27 @@ inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) /
 }  // namespace
 
 constexpr uint32_t MAX_BATCH = BWTC_CUDA_MAX_BATCH;  // blocks sorted as one text (6 key bits for the block number)
-constexpr uint32_t LF_PARK = MAX_BATCH * 256, LF_WATCH = LF_PARK + MAX_BATCH, LF_WORDS = LF_WATCH + 8;
+constexpr uint32_t LF_PARK = MAX_BATCH * 256, LF_WORDS = LF_PARK + MAX_BATCH + 8;
+// Pinned staging ring for PAGEABLE caller buffers (a malloc'ed PrecompressorBlock, PrecompressorBlock.cpp:37-49): the
+// worker thread copies chunk by chunk through it while the DMA engine moves the previous chunks, on copy streams of
+// their own.  Pinned caller buffers are copied directly.
+constexpr size_t RING_CHUNK = 4u << 20;
+constexpr int RING_SLOTS = 4;
 
 struct bwtc_cuda_ctx {
   int device = 0;
   int sm_count = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;     // kernels (+ the direct copies of pinned / device-resident caller buffers)
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // staged H2D / D2H of pageable caller buffers (pinned ring)
+  cudaEvent_t ev_sync = nullptr;     // host waits (blocking-sync event unless spin_wait)
+  cudaEvent_t ev_in = nullptr, ev_comp = nullptr;  // hand-off copy stream <-> kernel stream
+  cudaEvent_t ev_ring[RING_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  uint8_t* h_ring = nullptr;         // RING_SLOTS x RING_CHUNK pinned bytes, allocated on first use
+  uint64_t ring_next = 0;            // slots are handed out round-robin across calls ...
+  bool ring_busy[RING_SLOTS] = {false, false, false, false};  // ... and waited for (ev_ring) before they are reused
+  int poll_spin_us = 150, poll_sleep_us = 40;
+  int wait_mode = 0;                 // host waits: 0 adaptive (poll briefly, then sleep in short steps), 1 spin
+                                     // (cudaStreamSynchronize), 2 blocking-sync event
   uint32_t cap = 0;  // max block bytes (a batch: sum of block bytes + blocks - 1)
   size_t max_rs_tiles = 0, max_aux_tiles = 0;
   // ---- device memory
@@ -72,7 +92,9 @@ struct bwtc_cuda_ctx {
   uint32_t* d_tilecnt = nullptr;  // [2][max_aux_tiles]: per-tile live counts of k_rerank and their exclusive prefix,
                                   // then [max_aux_tiles][MAX_RERANK_WINDOWS+1] bucket offsets of the bucketed scatter
   uint32_t* d_LF = nullptr;       // [LF_PARK) LFpowers (one row of 256 per block of a batch), [LF_PARK + k] parked hole byte
-                                  // of block k, [LF_WATCH] watchdog word of k_small_rounds
+                                  // of block k
+  LadderState* d_state = nullptr; // device-side round control (bwt_kernels.cuh)
+  LadderState* h_state = nullptr; // ... its pinned host copy
   unsigned long long* d_wtab = nullptr;  // window-sample table: WS_SLOTS keys, WS_SLOTS counters, 2 doubles
   uint32_t* d_bhist = nullptr;    // [MAX_BATCH][256] per-block byte histograms of a batch
   const uint8_t** d_bptr = nullptr;  // [MAX_BATCH] device pointers to the blocks of a batch
@@ -89,6 +111,8 @@ struct bwtc_cuda_ctx {
                                   // if the spin watchdog ever fires
   int lb_watchdog = 0;            // the last transform failed on the look-back watchdog
   int debug_fake_watchdog = 0;    // test hook: pretend the watchdog fired while static tile ids are in use
+  int debug_reverse_tiles = 0;    // test hook: static tile ids in REVERSE dispatch order (a real violation)
+  int ladder_first = 2, ladder_more = 4;  // segmented rounds enqueued speculatively behind a sort round / per retry
   int use_seg = 1;                // segmented (sort-free) doubling rounds when every group is small
   int use_batch = 1;              // small equal-sized blocks of one call are sorted as one text
   int use_pack_pred = 1;          // carry code(T[id-1]) above the id through the round-0 sort when it fits
@@ -135,11 +159,20 @@ void ctx_free(bwtc_cuda_ctx* c) {
   cudaFree(c->d_keys[0]); cudaFree(c->d_keys[1]); cudaFree(c->d_idx[0]); cudaFree(c->d_idx[1]);
   cudaFree(c->d_zero); cudaFree(c->d_status); cudaFree(c->d_LF); cudaFree(c->d_wtab); cudaFree(c->d_tilecnt); cudaFree(c->d_scat);
   cudaFree(c->d_bhist); cudaFree(c->d_bptr); cudaFree(c->d_aux[0]); cudaFree(c->d_aux[1]);
+  cudaFree(c->d_state);
   if (c->h_batch) cudaFreeHost(c->h_batch);
   if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->h_state) cudaFreeHost(c->h_state);
+  if (c->h_ring) cudaFreeHost(c->h_ring);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
+  if (c->ev_sync) cudaEventDestroy(c->ev_sync);
+  if (c->ev_in) cudaEventDestroy(c->ev_in);
+  if (c->ev_comp) cudaEventDestroy(c->ev_comp);
+  for (cudaEvent_t e : c->ev_ring) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -237,6 +270,12 @@ uint32_t rerank_launches(const bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m) {
   return (ctx->bucket_min_windows && w >= (uint32_t)ctx->bucket_min_windows) ? 1u : w;
 }
 
+// Tile-id source of the look-back kernels: the block index (default), tickets, or the reversed debug map.
+inline uint32_t tile_slot(const bwtc_cuda_ctx* ctx, uint32_t ticket_word) {
+  if (!ctx->static_tiles) return ticket_word;
+  return ctx->debug_reverse_tiles ? CTR_STATIC_REV : CTR_STATIC;
+}
+
 struct PassTimer {
   bwtc_cuda_ctx* ctx;
   size_t used = 0;
@@ -275,12 +314,12 @@ int run_sort_impl(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first
     if (iota)
       k_radix_pass<KeyT, RS_BLOCK, IPT, true, AUX><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-          ctx->static_tiles ? CTR_STATIC : (uint32_t)(CTR_PASS0 + p), iota_top, pack_bits, topshift, pred_mask, nullptr,
+          tile_slot(ctx, (uint32_t)(CTR_PASS0 + p)), iota_top, pack_bits, topshift, pred_mask, nullptr,
           ctx->d_aux[cur ^ 1]);
     else
       k_radix_pass<KeyT, RS_BLOCK, IPT, false, AUX><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
           kin, ctx->d_idx[cur], kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-          ctx->static_tiles ? CTR_STATIC : (uint32_t)(CTR_PASS0 + p), iota_top, 0u, 0u, 0u, ctx->d_aux[cur], ctx->d_aux[cur ^ 1]);
+          tile_slot(ctx, (uint32_t)(CTR_PASS0 + p)), iota_top, 0u, 0u, 0u, ctx->d_aux[cur], ctx->d_aux[cur ^ 1]);
     CK(ctx, cudaGetLastError());
     if (pt->end()) return BWTC_CUDA_ECUDA;
     ctx->stats.kernel_launches++;
@@ -313,7 +352,9 @@ int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota
 
 int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m, uint32_t rs_tile, uint32_t pass_mask) {
   const uint32_t aux_tiles = div_up(m, AUX_TILE);
-  CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)rerank_launches(ctx, N, m) * ctx->max_aux_tiles * 8, ctx->stream));
+  CK(ctx, cudaMemsetAsync(ctx->d_zero + CTR_STICKY, 0,
+                          (size_t)(CTR_WORDS - CTR_STICKY + HIST_WORDS) * 4 + (size_t)rerank_launches(ctx, N, m) * ctx->max_aux_tiles * 8,
+                          ctx->stream));
   const uint32_t tiles = div_up(m, rs_tile);
   for (int p = 0; p < MAX_PASSES; ++p)
     if ((pass_mask >> p) & 1u)
@@ -338,14 +379,14 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
     const uint32_t win_ids = div_up(N, nwin);
     rp.win_lo = 0;
     rp.win_hi = 0xFFFFFFFFu;
-    rp.ctr_slot = ctx->static_tiles ? CTR_STATIC : (uint32_t)CTR_RERANK;
+    rp.ctr_slot = tile_slot(ctx, (uint32_t)CTR_RERANK);
     rp.nbuckets = nwin;
     rp.bucket_magic = (uint32_t)(((1ull << 32) + win_ids - 1) / win_ids);
     StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, 1, ctx->d_idx[cur ^ 1], ctx->d_scat, woff};
     k_rerank<KeyT, ROUND0><<<tiles, 256, 0, st>>>(keys, ctx->d_idx[cur], ctx->d_rank, rp, ctx->d_tstate(), ctx->d_ctrl(), ep, sp);
     const uint32_t grid = std::min<uint32_t>(div_up(tiles, 8), (uint32_t)ctx->sm_count * 8u);
     for (uint32_t b = 0; b < nwin; ++b)
-      k_scatter_bucket<<<grid, 256, 0, st>>>(ctx->d_idx[cur ^ 1], ctx->d_scat, woff, tiles, nwin, b, AUX_TILE, ctx->d_rank);
+      k_scatter_bucket<<<grid, 256, 0, st>>>(ctx->d_idx[cur ^ 1], ctx->d_scat, woff, tiles, nwin, b, AUX_TILE, ctx->d_rank, ctx->d_ctrl());
     CK(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += 1 + nwin;
     ctx->stats.algorithmic_bytes += (uint64_t)m * 16;  // staged (id, rank) pairs: written once, read once
@@ -354,7 +395,7 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
   for (uint32_t w = 0; w < nwin; ++w) {
     rp.win_lo = (uint32_t)((uint64_t)N * w / nwin);
     rp.win_hi = (w + 1 == nwin) ? 0xFFFFFFFFu : (uint32_t)((uint64_t)N * (w + 1) / nwin);
-    rp.ctr_slot = ctx->static_tiles ? CTR_STATIC : (uint32_t)(CTR_RERANK + w);
+    rp.ctr_slot = tile_slot(ctx, (uint32_t)(CTR_RERANK + w));
     rp.nbuckets = 0;
     rp.bucket_magic = 0;
     StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, w == 0 ? 1 : 0, nullptr, nullptr, nullptr};
@@ -379,66 +420,199 @@ struct BatchSpec {
 };
 constexpr int64_t BATCH_NEEDS_SINGLE = -1000;  // all 256 byte values present: no code left for the reserved sentinel
 
-// The engine proper.  block_mode: in = X (n block bytes), result n bytes.  raw: in = T (n bytes), result n bytes.
-// in_dev / out_dev: device pointers supplied by the caller (or nullptr -> staged through the context).
-// bs != nullptr: batch of blocks (block contract); h_in/h_out/in_dev/out_dev/LF/nLF/freqs come from *bs.
-int64_t run_transform_once(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, uint8_t* h_out, const uint8_t* in_dev,
-                           uint8_t* out_dev, uint32_t n, uint32_t* LF, uint32_t nLF, uint32_t* freqs, const BatchSpec* bs) {
+// One transform call: what the caller handed in, and what phase A (input + policy) learnt about it.
+struct Job {
+  bool block_mode = true;          // in = X (n block bytes), result n bytes;  false (raw): in = T (n bytes)
+  const uint8_t* h_in = nullptr;   // host buffers of a single block ...
+  uint8_t* h_out = nullptr;
+  const uint8_t* in_dev = nullptr; // ... or the caller's device buffers
+  uint8_t* out_dev = nullptr;
+  uint32_t n = 0;
+  uint32_t* LF = nullptr;
+  uint32_t nLF = 0;
+  uint32_t* freqs = nullptr;
+  const BatchSpec* bs = nullptr;   // batch of blocks (block contract): the fields above come from *bs
+  // ---- phase A
+  uint32_t N = 0, bstride = 0, blk_bits = 0;
+  bool sentinel_outside_alphabet = false;
+  bool present[256];
+  Round0Plan pl;
+  const uint8_t* d_text = nullptr;
+  uint8_t* d_dst = nullptr;
+  EmitParams ep;
+  uint64_t a_launches = 0, a_bytes = 0;  // kernel launches / algorithmic bytes of phase A
+};
+
+// Host wait for everything enqueued on `st` so far.  Default: sleep on a blocking-sync event — a waiting worker
+// costs no host core, so `depth` workers per GPU times 8 ranks do not oversubscribe the box.  BWTC_SPIN_WAIT=1 spins.
+int host_wait(bwtc_cuda_ctx* ctx, cudaStream_t st) {
+  if (ctx->wait_mode == 1) {
+    CK(ctx, cudaStreamSynchronize(st));
+    return 0;
+  }
+  CK(ctx, cudaEventRecord(ctx->ev_sync, st));
+  if (ctx->wait_mode == 2) {
+    CK(ctx, cudaEventSynchronize(ctx->ev_sync));
+    return 0;
+  }
+  // adaptive: a short busy poll catches the sub-100-us waits of a block running alone (a blocking-sync wake-up costs
+  // ~0.3 ms on a virtualised host: measured, profiles/r02_experiments.md); after that the thread sleeps in ~50 us steps,
+  // which costs a percent of a core however many blocks are in flight
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    const cudaError_t e = cudaEventQuery(ctx->ev_sync);
+    if (e == cudaSuccess) return 0;
+    if (e != cudaErrorNotReady) CK(ctx, e);
+    const auto dt = std::chrono::steady_clock::now() - t0;
+    if (dt > std::chrono::microseconds(ctx->poll_spin_us)) std::this_thread::sleep_for(std::chrono::microseconds(ctx->poll_sleep_us));
+  }
+}
+
+// wait for one ring slot's copy (host side)
+int ring_wait(bwtc_cuda_ctx* ctx, int slot) {
+  if (!ctx->ring_busy[slot]) return 0;
+  for (;;) {
+    const cudaError_t e = cudaEventQuery(ctx->ev_ring[slot]);
+    if (e == cudaSuccess) break;
+    if (e != cudaErrorNotReady) CK(ctx, e);
+    std::this_thread::yield();
+  }
+  ctx->ring_busy[slot] = false;
+  return 0;
+}
+
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_ring(bwtc_cuda_ctx* ctx) {
+  if (ctx->h_ring) return 0;
+  CK(ctx, cudaMallocHost((void**)&ctx->h_ring, RING_CHUNK * RING_SLOTS));
+  CK(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+  CK(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < RING_SLOTS; ++i)
+    CK(ctx, cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventBlockingSync | cudaEventDisableTiming));
+  return 0;
+}
+
+// Host -> device.  Pinned source: one async copy on the kernel stream.  Pageable source: chunks through the pinned
+// ring on the copy-in stream (the memcpy of chunk i+1 overlaps the DMA of chunk i); the kernel stream then waits
+// for the last chunk.
+int upload(bwtc_cuda_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n) {
+  if (!n) return 0;
+  if (is_pinned_host(h_src)) {
+    CK(ctx, cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+  }
+  if (ensure_ring(ctx)) return BWTC_CUDA_ECUDA;
+  for (size_t off = 0; off < n; off += RING_CHUNK) {
+    const size_t len = std::min(RING_CHUNK, n - off);
+    const int slot = (int)(ctx->ring_next++ % RING_SLOTS);
+    if (ring_wait(ctx, slot)) return BWTC_CUDA_ECUDA;  // (also across calls: the blocks of a batch are uploaded back to back)
+    uint8_t* stage = ctx->h_ring + (size_t)slot * RING_CHUNK;
+    memcpy(stage, h_src + off, len);
+    CK(ctx, cudaMemcpyAsync(d_dst + off, stage, len, cudaMemcpyHostToDevice, ctx->s_in));
+    CK(ctx, cudaEventRecord(ctx->ev_ring[slot], ctx->s_in));
+    ctx->ring_busy[slot] = true;
+  }
+  CK(ctx, cudaEventRecord(ctx->ev_in, ctx->s_in));
+  CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in, 0));
+  return 0;
+}
+
+// Device -> pageable host through the ring (blocking: returns when h_dst holds the bytes).  Everything enqueued on
+// the kernel stream so far is waited for on the device (event), not by the host.
+int download_staged(bwtc_cuda_ctx* ctx, uint8_t* h_dst, const uint8_t* d_src, size_t n) {
+  if (!n) return 0;
+  if (ensure_ring(ctx)) return BWTC_CUDA_ECUDA;
+  CK(ctx, cudaEventRecord(ctx->ev_comp, ctx->stream));
+  CK(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp, 0));
+  for (int sl = 0; sl < RING_SLOTS; ++sl)
+    if (ring_wait(ctx, sl)) return BWTC_CUDA_ECUDA;  // uploads that still read the ring
+  const size_t nchunks = (n + RING_CHUNK - 1) / RING_CHUNK;
+  const uint64_t base = ctx->ring_next;
+  size_t issued = 0, done = 0;
+  while (done < nchunks) {
+    while (issued < nchunks && issued - done < (size_t)RING_SLOTS) {
+      const int slot = (int)((base + issued) % RING_SLOTS);
+      const size_t off = issued * RING_CHUNK, len = std::min(RING_CHUNK, n - off);
+      CK(ctx, cudaMemcpyAsync(ctx->h_ring + (size_t)slot * RING_CHUNK, d_src + off, len, cudaMemcpyDeviceToHost, ctx->s_out));
+      CK(ctx, cudaEventRecord(ctx->ev_ring[slot], ctx->s_out));
+      ctx->ring_busy[slot] = true;
+      ++issued;
+    }
+    const int slot = (int)((base + done) % RING_SLOTS);
+    const size_t off = done * RING_CHUNK, len = std::min(RING_CHUNK, n - off);
+    if (ring_wait(ctx, slot)) return BWTC_CUDA_ECUDA;
+    memcpy(h_dst + off, ctx->h_ring + (size_t)slot * RING_CHUNK, len);
+    ++done;
+  }
+  ctx->ring_next = base + nchunks;
+  return 0;
+}
+
+// ---- phase A: input upload, reversed text + byte histogram, key-shape policy.  ONE host synchronisation (the plan
+// needs the block's alphabet).  Nothing is written to the caller's arrays.
+int64_t phase_input(bwtc_cuda_ctx* ctx, Job& J) {
   ctx->err[0] = 0;
-  ctx->lb_watchdog = 0;
   if (cudaSetDevice(ctx->device) != cudaSuccess) {
     set_err(ctx->err, "cudaSetDevice(%d) failed", ctx->device);
     return BWTC_CUDA_ECUDA;
   }
-  const uint32_t bstride = bs ? bs->n0 + 1u : 0u;
+  const BatchSpec* bs = J.bs;
+  J.bstride = bs ? bs->n0 + 1u : 0u;
   if (bs) {
-    n = (bs->nblocks - 1u) * bstride + bs->n_last;  // N - 1
-    nLF = bs->nLF;
-    LF = bs->LF;
-    freqs = bs->freqs;
+    J.n = (bs->nblocks - 1u) * J.bstride + bs->n_last;  // N - 1
+    J.nLF = bs->nLF;
+    J.LF = bs->LF;
+    J.freqs = bs->freqs;
   }
-  const uint32_t N = block_mode ? n + 1 : n;
+  const uint32_t n = J.n;
+  const uint32_t N = J.block_mode ? n + 1 : n;
+  J.N = N;
   if (n > ctx->cap) {
     set_err(ctx->err, "block of %u bytes exceeds context capacity %u", n, ctx->cap);
     return BWTC_CUDA_ETOOBIG;
   }
-  if (nLF < 1 || nLF > 256 || nLF > N || !LF) {
-    set_err(ctx->err, "bad nLFpowers %u for %u suffixes", nLF, N);
+  if (J.nLF < 1 || J.nLF > 256 || J.nLF > N || !J.LF) {
+    set_err(ctx->err, "bad nLFpowers %u for %u suffixes", J.nLF, N);
     return BWTC_CUDA_EARG;
   }
   cudaStream_t st = ctx->stream;
   bwtc_cuda_stats& S = ctx->stats;
   memset(&S, 0, sizeof(S));
   S.n_suffixes = N;
-  PassTimer pt{ctx};
 
   // ---- input
-  const uint8_t* d_src = in_dev;
+  const uint8_t* d_src = J.in_dev;
   const void** h_bptr = reinterpret_cast<const void**>(ctx->h_batch);
   uint32_t* h_bhist = reinterpret_cast<uint32_t*>(ctx->h_batch + MAX_BATCH * sizeof(void*));
-  uint32_t* h_bLF = h_bhist + MAX_BATCH * 256;
   if (bs) {
     for (uint32_t k = 0; k < bs->nblocks; ++k) {
       const uint32_t nk = (k + 1 == bs->nblocks) ? bs->n_last : bs->n0;
       if (bs->on_device) {
         h_bptr[k] = bs->in[k];
       } else {
-        CK(ctx, cudaMemcpyAsync(ctx->d_in + (size_t)k * bs->n0, bs->in[k], nk, cudaMemcpyHostToDevice, st));
+        if (upload(ctx, ctx->d_in + (size_t)k * bs->n0, static_cast<const uint8_t*>(bs->in[k]), nk)) return BWTC_CUDA_ECUDA;
         h_bptr[k] = ctx->d_in + (size_t)k * bs->n0;
       }
     }
     CK(ctx, cudaMemcpyAsync(ctx->d_bptr, h_bptr, bs->nblocks * sizeof(void*), cudaMemcpyHostToDevice, st));
     d_src = ctx->d_text;  // the policy sample reads the (reversed) concatenation
-  } else if (!in_dev) {
-    CK(ctx, cudaMemcpyAsync(ctx->d_in, h_in, n, cudaMemcpyHostToDevice, st));
+  } else if (!J.in_dev) {
+    if (upload(ctx, ctx->d_in, J.h_in, n)) return BWTC_CUDA_ECUDA;
     d_src = ctx->d_in;
   }
-  uint8_t* d_dst = (out_dev && !bs) ? out_dev : ctx->d_out;
+  J.d_dst = (J.out_dev && !bs) ? J.out_dev : ctx->d_out;
   CK(ctx, cudaEventRecord(ctx->ev_begin, st));
 
   // ---- byte histogram (+ reversed, sentinel-terminated text in block mode)
   CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)(CTR_WORDS + HIST_WORDS) * 4, st));
-  const uint8_t* d_text;
   const int pgrid = ctx->sm_count * 8;
   if (bs) {
     const uint32_t padded_words = div_up((uint64_t)N + TEXT_PAD, 4);
@@ -446,23 +620,23 @@ int64_t run_transform_once(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h
     const dim3 grid(std::max<uint32_t>(1u, div_up((uint32_t)pgrid, bs->nblocks)), bs->nblocks);
     k_prep_batch<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t* const*>(ctx->d_bptr), bs->n0, bs->n_last, bs->nblocks,
                                        ctx->d_text, N, padded_words, ctx->d_bhist);
-    d_text = ctx->d_text;
+    J.d_text = ctx->d_text;
     S.algorithmic_bytes += 2ull * n + N;
-  } else if (block_mode) {
+  } else if (J.block_mode) {
     const uint32_t padded_words = div_up((uint64_t)N + TEXT_PAD, 4);
     k_prep_block<<<pgrid, 256, 0, st>>>(d_src, n, ctx->d_text, padded_words, ctx->d_hist());
-    d_text = ctx->d_text;
+    J.d_text = ctx->d_text;
     S.algorithmic_bytes += (uint64_t)n + N;
   } else {
     k_hist_bytes<<<pgrid, 256, 0, st>>>(d_src, N - 1, ctx->d_hist());
-    d_text = d_src;
+    J.d_text = d_src;
     S.algorithmic_bytes += (uint64_t)N;
   }
   CK(ctx, cudaGetLastError());
   S.kernel_launches++;
   double* d_pairs = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ctx->d_wtab) + (size_t)WS_SLOTS * 12);
   {  // sampled 8-byte-window collision statistics for the key-shape policy
-    const uint32_t nbytes = block_mode ? n : N;
+    const uint32_t nbytes = J.block_mode ? n : N;
     uint32_t* d_cnt = reinterpret_cast<uint32_t*>(ctx->d_wtab + WS_SLOTS);
     CK(ctx, cudaMemsetAsync(ctx->d_wtab, 0xFF, (size_t)WS_SLOTS * 8, st));
     CK(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)WS_SLOTS * 4 + 16, st));
@@ -479,59 +653,78 @@ int64_t run_transform_once(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h
   }
   if (bs) CK(ctx, cudaMemcpyAsync(h_bhist, ctx->d_bhist, (size_t)bs->nblocks * 256 * 4, cudaMemcpyDeviceToHost, st));
   else CK(ctx, cudaMemcpyAsync(ctx->h_hist(), ctx->d_hist(), 256 * 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));
+  if (host_wait(ctx, st)) return BWTC_CUDA_ECUDA;
 
   uint64_t count[256];
-  bool present[256];
   uint32_t npresent = 0;
   for (int c = 0; c < 256; ++c) {
     count[c] = 0;
     if (bs) for (uint32_t k = 0; k < bs->nblocks; ++k) count[c] += h_bhist[k * 256 + c];
     else count[c] = ctx->h_hist()[c];
-    present[c] = count[c] != 0;
-    npresent += present[c] ? 1u : 0u;
+    J.present[c] = count[c] != 0;
+    npresent += J.present[c] ? 1u : 0u;
   }
-  if (bs && npresent >= 256) return BATCH_NEEDS_SINGLE;  // nothing has been written to the caller's arrays yet
-  if (freqs) {
-    for (int c = 0; c < 256; ++c) {
-      if (bs) for (uint32_t k = 0; k < bs->nblocks; ++k) freqs[k * 256 + c] += h_bhist[k * 256 + c];
-      else freqs[c] += ctx->h_hist()[c];
-    }
-  }
+  if (bs && npresent >= 256) return BATCH_NEEDS_SINGLE;
   // Block contract: the appended 0x00 only enters the alphabet if the block itself contains 0x00.  Otherwise
   // it is a true sentinel: it gets code 0 like the padding past the end, and the "window ran past the end"
   // rule of the round-0 re-rank starts one position earlier — a 4-letter alphabet then packs
   // into 2 bits per character instead of 3.  A batch reserves code 0 for its sentinels instead (§3.6).
-  bool sentinel_outside_alphabet = false;
-  uint32_t blk_bits = 0;
+  J.sentinel_outside_alphabet = false;
+  J.blk_bits = 0;
   if (bs) {
-    blk_bits = std::max<uint32_t>(1u, (uint32_t)ceil_log2_u64(bs->nblocks));
-  } else if (block_mode) {
-    if (!present[0]) sentinel_outside_alphabet = true;
+    J.blk_bits = std::max<uint32_t>(1u, (uint32_t)ceil_log2_u64(bs->nblocks));
+  } else if (J.block_mode) {
+    if (!J.present[0]) J.sentinel_outside_alphabet = true;
   } else {
-    const uint8_t last = h_in[N - 1];
-    present[last] = true;
+    const uint8_t last = J.h_in[N - 1];
+    J.present[last] = true;
     count[last] += 1;
   }
-
   double pair_stats[2];  // [0] colliding pairs among the sampled 8-byte windows, [1] samples
   memcpy(pair_stats, ctx->h_LF() + 256, 16);
-  Round0Plan pl;
-  plan_round0(ctx, count, present, N, pair_stats, &pl, blk_bits);
-  if (bs) { pl.pp.nblocks = bs->nblocks; pl.pp.stride = bstride; }
-  EmitParams ep;
-  ep.nblocks = bs ? bs->nblocks : 1u;
-  ep.stride = bstride;
-  ep.text = d_text;
-  ep.out = d_dst;
-  ep.lastch = ctx->d_LF + LF_PARK;
-  ep.N = N;
-  ep.block_mode = block_mode ? 1 : 0;
-  CK(ctx, cudaMemsetAsync(ctx->d_LF + LF_PARK, 0, (size_t)(LF_WORDS - LF_PARK) * 4, st));  // parked hole bytes, tail-kernel watchdog
-  S.sigma = pl.sigma;
-  S.bits_per_char = pl.bits;
-  S.chars_round0 = pl.chars;
-  S.key_bytes_round0 = pl.keybytes;
+  plan_round0(ctx, count, J.present, N, pair_stats, &J.pl, J.blk_bits);
+  if (bs) { J.pl.pp.nblocks = bs->nblocks; J.pl.pp.stride = J.bstride; }
+  J.ep.nblocks = bs ? bs->nblocks : 1u;
+  J.ep.stride = J.bstride;
+  J.ep.text = J.d_text;
+  J.ep.out = J.d_dst;
+  J.ep.lastch = ctx->d_LF + LF_PARK;
+  J.ep.N = N;
+  J.ep.block_mode = J.block_mode ? 1 : 0;
+  S.sigma = J.pl.sigma;
+  S.bits_per_char = J.pl.bits;
+  S.chars_round0 = J.pl.chars;
+  S.key_bytes_round0 = J.pl.keybytes;
+  J.a_launches = S.kernel_launches;
+  J.a_bytes = S.algorithmic_bytes;
+  return 0;
+}
+
+// ---- phase B: round 0, the device-controlled ladder of sort-free rounds, host-driven global radix rounds where
+// groups are large, final extraction, result copies.  Works from ctx->d_text only, so it can be repeated (with ticket
+// tile ids) after a look-back watchdog without the caller's input.
+int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
+  ctx->lb_watchdog = 0;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) {
+    set_err(ctx->err, "cudaSetDevice(%d) failed", ctx->device);
+    return BWTC_CUDA_ECUDA;
+  }
+  cudaStream_t st = ctx->stream;
+  bwtc_cuda_stats& S = ctx->stats;
+  const BatchSpec* bs = J.bs;
+  const uint32_t N = J.N, n = J.n;
+  const Round0Plan& pl = J.pl;
+  const EmitParams& ep = J.ep;
+  const uint8_t* d_text = J.d_text;
+  PassTimer pt{ctx};
+  // a repeated phase B starts its statistics over (phase A's launches and bytes are kept)
+  S.kernel_launches = J.a_launches;
+  S.algorithmic_bytes = J.a_bytes;
+  S.sort_bytes = S.sort0_bytes = 0;
+  S.sort_launches = S.sort0_launches = 0;
+  CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)CTR_STICKY * 4, st));  // sticky control words (CTR_ERR)
+  CK(ctx, cudaMemsetAsync(ctx->d_state, 0, sizeof(LadderState), st));
+  CK(ctx, cudaMemsetAsync(ctx->d_LF + LF_PARK, 0, (size_t)(LF_WORDS - LF_PARK) * 4, st));  // parked hole bytes
 
   // ---- round 0: pack keys (+ all digit histograms), sort, re-rank
   const uint32_t rs_tile0 = pl.keybytes == 4 ? RS_TILE32 : RS_TILE64;
@@ -608,7 +801,7 @@ int64_t run_transform_once(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h
     RerankParams rp;
     rp.m = N;
     {
-      const uint32_t text_end = sentinel_outside_alphabet ? N - 1 : N;  // windows reaching text_end are unique
+      const uint32_t text_end = J.sentinel_outside_alphabet ? N - 1 : N;  // windows reaching text_end are unique
       rp.short_thresh = pl.chars > text_end ? 0u : text_end - pl.chars + 1u;
     }
     rp.lo_bits = 0;
@@ -619,128 +812,181 @@ int64_t run_transform_once(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h
     rp.id_mask = pack_pred ? (uint32_t)((1ull << id_bits) - 1ull) : 0xFFFFFFFFu;
     memset(rp.decode, 0, sizeof(rp.decode));
     for (int c = 0; c < 256; ++c)
-      if (present[c]) rp.decode[pl.pp.lut[c]] = (uint8_t)c;
+      if (J.present[c]) rp.decode[pl.pp.lut[c]] = (uint8_t)c;
     uint32_t* snr = reinterpret_cast<uint32_t*>(ctx->d_keys[cur ^ 1]);
     if (pl.keybytes == 4) rc = launch_rerank<uint32_t, true>(ctx, cur, N, N, rp, ep, snr, snr + N);
     else rc = launch_rerank<unsigned long long, true>(ctx, cur, N, N, rp, ep, snr, snr + N);
     if (rc) return rc;
     S.algorithmic_bytes += (uint64_t)N * (pl.keybytes + 4) + (uint64_t)N * 4;
   }
-  CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_WORDS * 4, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));
-  if (ctx->h_ctrl()[CTR_ERR] || (ctx->debug_fake_watchdog && ctx->static_tiles)) {
-    set_err(ctx->err, "look-back watchdog fired in round 0 (code %u)", ctx->h_ctrl()[CTR_ERR]);
-    ctx->lb_watchdog = 1;
-    return BWTC_CUDA_EINTERNAL;
-  }
-  uint32_t live = ctx->h_ctrl()[CTR_LIVE];
-  uint32_t maxgroup = ctx->h_ctrl()[CTR_MAXGROUP];
-  uint32_t m_prev = N;  // records of the last global sort = extent of the k_rerank staging slots
   // six u32[N] work arrays: halves of the two key buffers and the two id buffers
-  uint32_t* pool[6] = {reinterpret_cast<uint32_t*>(ctx->d_keys[0]), reinterpret_cast<uint32_t*>(ctx->d_keys[0]) + N,
-                       reinterpret_cast<uint32_t*>(ctx->d_keys[1]), reinterpret_cast<uint32_t*>(ctx->d_keys[1]) + N,
-                       ctx->d_idx[0], ctx->d_idx[1]};
-  int list_nr = -1, list_id = -1;  // pool indices of the compact, rank-ordered (rank, id) lists of the live suffixes
-  bool have_lists = false, after_seg = false;
+  PoolPtrs pool;
+  pool.p[0] = reinterpret_cast<uint32_t*>(ctx->d_keys[0]);
+  pool.p[1] = reinterpret_cast<uint32_t*>(ctx->d_keys[0]) + N;
+  pool.p[2] = reinterpret_cast<uint32_t*>(ctx->d_keys[1]);
+  pool.p[3] = reinterpret_cast<uint32_t*>(ctx->d_keys[1]) + N;
+  pool.p[4] = ctx->d_idx[0];
+  pool.p[5] = ctx->d_idx[1];
   ctx->last_cur = cur;
+  uint32_t m_prev = N;       // records of the last global sort = extent of the k_rerank staging slots
+  uint32_t m_bound = N;      // upper bound of the live count (it never grows)
+  uint64_t h_next = pl.chars;
+  auto sel_of = [](int c) { return (uint32_t)(2 * c) | ((uint32_t)(2 * c + 1) << 4); };
+  k_commit_sort<<<1, 1, 0, st>>>(ctx->d_state, ctx->d_ctrl(), (uint32_t)std::min<uint64_t>(h_next, 0x7FFFFFFFull), sel_of(cur),
+                                 0xFFFFFFFFu);
+  S.kernel_launches++;
 
   // Concatenate the per-tile chunks k_rerank staged (in d_keys[cur^1]) into compact lists in d_keys[cur], whose
-  // sorted keys are dead by now.  Tile order is kept, so every group stays contiguous.
-  auto make_lists = [&]() -> int {
+  // sorted keys are dead by now.  Tile order is kept, so every group stays contiguous.  speculative: the gather
+  // runs only if the device-side state says the next step consumes the lists.
+  auto make_lists = [&](bool speculative) -> int {
     const uint32_t tiles = div_up(m_prev, AUX_TILE);
     k_scan_tile_counts<<<1, 1024, 0, st>>>(ctx->d_tilecnt, ctx->d_tilecnt + ctx->max_aux_tiles, tiles);
-    k_gather_chunks<<<tiles, 256, 0, st>>>(pool[2 * (cur ^ 1)], pool[2 * (cur ^ 1) + 1], ctx->d_tilecnt,
-                                           ctx->d_tilecnt + ctx->max_aux_tiles, AUX_TILE, pool[2 * cur], pool[2 * cur + 1]);
+    k_gather_chunks<<<tiles, 256, 0, st>>>(pool.p[2 * (cur ^ 1)], pool.p[2 * (cur ^ 1) + 1], ctx->d_tilecnt,
+                                           ctx->d_tilecnt + ctx->max_aux_tiles, AUX_TILE, pool.p[2 * cur], pool.p[2 * cur + 1],
+                                           speculative ? ctx->d_state : nullptr, ctx->d_ctrl());
     CK(ctx, cudaGetLastError());
     S.kernel_launches += 2;
-    S.algorithmic_bytes += (uint64_t)live * 16;
-    list_nr = 2 * cur;
-    list_id = 2 * cur + 1;
-    have_lists = true;
     return 0;
   };
 
-  // ---- doubling rounds
+  // Result copies that need no host staging: pinned host buffers and device buffers.  Enqueued speculatively behind the
+  // first ladder chunk (a block whose later rounds are all sort-free then completes with one host wait); repeated at
+  // the end if the block was not finished by then.
+  const bool direct_out = bs ? (bs->on_device || is_pinned_host(bs->out[0]))
+                             : (J.out_dev != nullptr || (J.block_mode && J.h_out && is_pinned_host(J.h_out)));
+  uint32_t* h_bLF = reinterpret_cast<uint32_t*>(ctx->h_batch + MAX_BATCH * sizeof(void*)) + MAX_BATCH * 256;
+  auto enqueue_direct_out = [&]() -> int {
+    if (bs) {
+      for (uint32_t k = 0; k < bs->nblocks; ++k) {  // block k's BWT bytes are out[k*stride .. k*stride + n_k)
+        const uint32_t nk = (k + 1 == bs->nblocks) ? bs->n_last : bs->n0;
+        CK(ctx, cudaMemcpyAsync(bs->out[k], ctx->d_out + (size_t)k * J.bstride, nk,
+                                bs->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+      }
+    } else if (!J.out_dev) {
+      CK(ctx, cudaMemcpyAsync(J.h_out, ctx->d_out, n, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+  };
+
   const int lo_bits = (int)ceil_log2_u64((uint64_t)N + 1);  // rank[i+h] + 1 in [0, N]
   // high part = (rank of the group head) >> 1 (k_build_keys): heads of live groups are <= N - 2
   const int hi_bits = N > 3 ? (int)ceil_log2_u64((((uint64_t)N - 2) >> 1) + 1) : 1;
   const uint32_t npassd = div_up((uint64_t)(lo_bits + hi_bits), 8);
   const uint32_t maskd = (1u << npassd) - 1u;
-  uint64_t h = pl.chars;
-  while (live > 0) {
-    if (ctx->debug_max_rounds && S.rounds >= ctx->debug_max_rounds) break;
-    if (S.rounds >= BWTC_CUDA_MAX_ROUNDS || h >= 2ull * N + 2) {
-      set_err(ctx->err, "prefix doubling did not converge (round %u, h %llu, live %u)", S.rounds, (unsigned long long)h, live);
-      return BWTC_CUDA_EINTERNAL;
-    }
-    const uint32_t r = S.rounds;
-    const uint32_t m = live;
-    const uint32_t h32 = (uint32_t)(h > 0x7FFFFFFFull ? 0x7FFFFFFFull : h);
-
-    if (m <= (uint32_t)SMALL_MAX) {
-      // tail: one CTA finishes all remaining rounds on the device
-      if (!have_lists && make_lists()) return BWTC_CUDA_ECUDA;
-      k_small_rounds<<<1, 1024, 0, st>>>(pool[list_id], m, ctx->d_rank, N, h32, ep, ctx->d_LF + LF_WATCH);
-      CK(ctx, cudaGetLastError());
-      S.kernel_launches++;
-      S.algorithmic_bytes += (uint64_t)m * 24;
-      S.live[r] = m;
-      S.passes[r] = 0;
-      S.prefix_len[r] = h32;
-      S.rounds = r + 1;
-      live = 0;
-      break;
-    }
-
-    if (ctx->use_seg && maxgroup <= (uint32_t)SEG_MAXGROUP) {
-      // every group is small: order each group locally, no global sort (k_seg_round + k_apply_ranks)
-      if (!have_lists && make_lists()) return BWTC_CUDA_ECUDA;
-      int free_idx[4], nf = 0;
-      for (int q = 0; q < 6; ++q)
-        if (q != list_nr && q != list_id) free_idx[nf++] = q;
-      const int out_nr = free_idx[0], out_id = free_idx[1], up_a = free_idx[2], up_b = free_idx[3];
-      CK(ctx, cudaMemsetAsync(ctx->d_ctrl(), 0, CTR_WORDS * 4, st));
-      k_seg_round<<<div_up(m, SEG_T), 256, 0, st>>>(pool[list_nr], pool[list_id], m, ctx->d_rank, N, h32, ep, pool[out_nr],
-                                                    pool[out_id], pool[up_a], pool[up_b], ctx->d_ctrl());
-      k_apply_ranks<<<ctx->sm_count * 8, 256, 0, st>>>(pool[up_a], pool[up_b], ctx->d_ctrl(), ctx->d_rank);
-      CK(ctx, cudaGetLastError());
-      S.kernel_launches += 2;
-      S.algorithmic_bytes += (uint64_t)m * 32;
-      CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_WORDS * 4, cudaMemcpyDeviceToHost, st));
-      CK(ctx, cudaStreamSynchronize(st));
-      if (ctx->h_ctrl()[CTR_ERR]) {
-        set_err(ctx->err, "segmented round %u failed (code %u)", r, ctx->h_ctrl()[CTR_ERR]);
-        return BWTC_CUDA_EINTERNAL;
+  bool lists_pending = true, first_chunk = true, out_enqueued = false, finished = false;
+  uint32_t nlog_seen = 0;
+  const uint32_t dbg = ctx->debug_max_rounds;
+  for (;;) {
+    // ---- one ladder chunk: [lists] [K x (segmented round, rank update, commit)] [tail] [finish] [copies]
+    const bool chunk_built_lists = lists_pending;
+    if (!(dbg && S.rounds >= dbg)) {
+      if (lists_pending) {
+        if (make_lists(true)) return BWTC_CUDA_ECUDA;
+        lists_pending = false;
       }
-      S.live[r] = m;
-      S.passes[r] = 0;
-      S.prefix_len[r] = h32;
-      S.rounds = r + 1;
-      live = ctx->h_ctrl()[CTR_LIVE];
-      maxgroup = ctx->h_ctrl()[CTR_MAXGROUP];
-      list_nr = out_nr;
-      list_id = out_id;
-      after_seg = true;
-      h *= 2;
-      continue;
+      const int K = dbg ? 1 : (first_chunk ? ctx->ladder_first : ctx->ladder_more);
+      const uint32_t seg_grid = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(m_bound, SEG_T), (uint32_t)ctx->sm_count * 16u));
+      for (int k = 0; k < K && ctx->use_seg; ++k) {
+        k_seg_round<<<seg_grid, 256, 0, st>>>(ctx->d_state, pool, ctx->d_rank, N, ep, ctx->d_ctrl());
+        k_apply_ranks<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_state, pool, ctx->d_ctrl(), ctx->d_rank);
+        k_commit_seg<<<1, 1, 0, st>>>(ctx->d_state, ctx->d_ctrl());
+        S.kernel_launches += 3;
+      }
+      if (!dbg) {
+        k_small_rounds<<<1, 1024, 0, st>>>(ctx->d_state, pool, ctx->d_rank, N, ep, ctx->d_ctrl());
+        S.kernel_launches++;
+      }
+      CK(ctx, cudaGetLastError());
     }
-
-    if (after_seg) {  // group sizes never grow, so a segmented round is never followed by a global sort
-      set_err(ctx->err, "internal: global sort requested after a segmented round (maxgroup %u)", maxgroup);
+    // final extraction: pidx, LFpowers, hole fill (returns early on the device while suffixes are still live)
+    if (bs)
+      k_finish_batch<<<bs->nblocks, 256, 0, st>>>(ctx->d_rank, N, J.bstride, bs->nblocks, J.d_dst, ctx->d_LF, bs->nLF, bs->nLF_last,
+                                                  ctx->d_LF + LF_PARK, ctx->d_state, ctx->d_ctrl());
+    else
+      k_finish<<<1, 256, 0, st>>>(ctx->d_rank, d_text, N, J.d_dst, J.block_mode ? 1 : 0, ctx->d_LF, J.nLF, ctx->d_LF + LF_PARK,
+                                  ctx->d_state, ctx->d_ctrl());
+    CK(ctx, cudaGetLastError());
+    S.kernel_launches++;
+    CK(ctx, cudaEventRecord(ctx->ev_end, st));
+    CK(ctx, cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LadderState), cudaMemcpyDeviceToHost, st));
+    if (bs) CK(ctx, cudaMemcpyAsync(h_bLF, ctx->d_LF, (size_t)bs->nblocks * 256 * 4, cudaMemcpyDeviceToHost, st));
+    else CK(ctx, cudaMemcpyAsync(ctx->h_LF(), ctx->d_LF, J.nLF * 4, cudaMemcpyDeviceToHost, st));
+    if (first_chunk && direct_out && !dbg) {
+      if (enqueue_direct_out()) return BWTC_CUDA_ECUDA;
+      out_enqueued = true;
+    }
+    if (host_wait(ctx, st)) return BWTC_CUDA_ECUDA;
+    const LadderState& H = *ctx->h_state;
+    if (H.err == 4u) {
+      set_err(ctx->err, "segmented round met a group above its limit (internal error)");
       return BWTC_CUDA_EINTERNAL;
     }
-    // ---- global radix round
+    if (H.err == 5u) {
+      set_err(ctx->err, "k_build_keys emitted a record count that differs from the live count (internal error)");
+      return BWTC_CUDA_EINTERNAL;
+    }
+    if (H.err == 3u) {
+      set_err(ctx->err, "tail refinement kernel did not converge");
+      return BWTC_CUDA_EINTERNAL;
+    }
+    if (H.err || (ctx->debug_fake_watchdog && ctx->static_tiles)) {
+      set_err(ctx->err, "look-back watchdog fired (code %u, round %u)", H.err, S.rounds);
+      ctx->lb_watchdog = 1;
+      return BWTC_CUDA_EINTERNAL;
+    }
+    // rounds the device executed in this chunk
+    for (uint32_t i = nlog_seen; i < H.nlog && i < (uint32_t)LADDER_LOG; ++i) {
+      const uint32_t r = S.rounds;
+      if (chunk_built_lists && i == nlog_seen) S.algorithmic_bytes += (uint64_t)H.log_m[i] * 16;  // k_gather_chunks
+      if (r < BWTC_CUDA_MAX_ROUNDS) {
+        S.live[r] = H.log_m[i];
+        S.passes[r] = 0;
+        S.prefix_len[r] = H.log_h[i];
+        S.rounds = r + 1;
+      }
+      S.algorithmic_bytes += (uint64_t)H.log_m[i] * (H.log_kind[i] == 1u ? 32u : 24u);
+    }
+    nlog_seen = H.nlog;
+    first_chunk = false;
+    if (H.m == 0) { finished = true; break; }
+    out_enqueued = false;  // the speculative copies ran before the block was complete: repeat them at the end
+    if (dbg && S.rounds >= dbg) break;
+    const uint32_t m = H.m;
+    m_bound = m;
+    if (S.rounds >= BWTC_CUDA_MAX_ROUNDS - 1 || (uint64_t)H.h >= 2ull * N + 2) {
+      set_err(ctx->err, "prefix doubling did not converge (round %u, h %u, live %u)", S.rounds, H.h, m);
+      return BWTC_CUDA_EINTERNAL;
+    }
+    if (ctx->use_seg && H.lists && H.maxgroup <= (uint32_t)SEG_MAXGROUP) continue;  // more segmented rounds than were enqueued
+    if (m <= (uint32_t)SMALL_MAX && !dbg) {
+      set_err(ctx->err, "internal: tail kernel skipped %u live suffixes", m);
+      return BWTC_CUDA_EINTERNAL;
+    }
+
+    // ---- global radix round (large groups: repetitive input), host-driven
+    const uint32_t r = S.rounds;
+    const uint32_t h32 = H.h;
     const bool from_list = ((uint64_t)m * 8 <= (uint64_t)N);
-    if (from_list && !have_lists && make_lists()) return BWTC_CUDA_ECUDA;
+    const bool have_lists = H.lists != 0;
+    if (have_lists && H.sel != sel_of(cur)) {  // group sizes never grow, so a segmented round is never followed by a global sort
+      set_err(ctx->err, "internal: global sort requested after a segmented round (maxgroup %u)", H.maxgroup);
+      return BWTC_CUDA_EINTERNAL;
+    }
     if (zero_round_state(ctx, N, m, RS_TILE64, maskd)) return BWTC_CUDA_ECUDA;
+    uint32_t expect_cursor = 0xFFFFFFFFu;
     if (from_list) {
+      if (!have_lists) {
+        if (make_lists(false)) return BWTC_CUDA_ECUDA;
+        S.algorithmic_bytes += (uint64_t)m * 16;
+      }
       // few live suffixes: gather-build from the id list (in d_keys[cur]) into the other buffer pair
       const int tb = cur ^ 1;
       const uint32_t bt = div_up(m, 256);
       const int grid = (int)(bt < (uint32_t)(ctx->sm_count * 8) ? bt : (uint32_t)(ctx->sm_count * 8));
-      k_build_from_list<<<grid, 256, 0, st>>>(pool[list_id], m, ctx->d_rank, N, h32, lo_bits,
+      k_build_from_list<<<grid, 256, 0, st>>>(pool.p[2 * cur + 1], m, ctx->d_rank, N, h32, lo_bits,
                                               static_cast<unsigned long long*>(ctx->d_keys[tb]), ctx->d_idx[tb],
-                                              ctx->d_hist(), (int)npassd);
+                                              ctx->d_hist(), (int)npassd, ctx->d_ctrl());
       CK(ctx, cudaGetLastError());
       S.kernel_launches++;
       S.algorithmic_bytes += (uint64_t)m * (4 + 8 + 12);
@@ -754,8 +1000,8 @@ int64_t run_transform_once(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h
       S.kernel_launches++;
       S.algorithmic_bytes += (uint64_t)N * 4 + (uint64_t)m * 12;
       cur = 0;
+      expect_cursor = m;
     }
-    have_lists = false;
     rc = run_sort<unsigned long long, RS_IPT64>(ctx, m, maskd, false, 0, &cur, &pt, &pdone);
     if (rc) return rc;
     {
@@ -767,68 +1013,72 @@ int64_t run_transform_once(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h
       rp.pred_aux = nullptr;
       rp.id_bits = 31;
       rp.id_mask = 0xFFFFFFFFu;
-      rc = launch_rerank<unsigned long long, false>(ctx, cur, m, N, rp, ep, pool[2 * (cur ^ 1)], pool[2 * (cur ^ 1) + 1]);
+      rc = launch_rerank<unsigned long long, false>(ctx, cur, m, N, rp, ep, pool.p[2 * (cur ^ 1)], pool.p[2 * (cur ^ 1) + 1]);
       if (rc) return rc;
       S.algorithmic_bytes += (uint64_t)m * 12 + (uint64_t)m * 4;
     }
-    CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_WORDS * 4, cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaStreamSynchronize(st));
-    if (ctx->h_ctrl()[CTR_ERR]) {
-      set_err(ctx->err, "look-back watchdog fired in round %u (code %u)", r, ctx->h_ctrl()[CTR_ERR]);
-      ctx->lb_watchdog = 1;
-      return BWTC_CUDA_EINTERNAL;
-    }
-    if (!from_list && ctx->h_ctrl()[CTR_CURSOR] != m) {
-      set_err(ctx->err, "round %u: k_build_keys emitted %u records, expected %u", r, ctx->h_ctrl()[CTR_CURSOR], m);
-      return BWTC_CUDA_EINTERNAL;
-    }
-    S.live[r] = m;
-    S.passes[r] = pdone;
-    S.prefix_len[r] = h32;
-    S.rounds = r + 1;
-    live = ctx->h_ctrl()[CTR_LIVE];
-    maxgroup = ctx->h_ctrl()[CTR_MAXGROUP];
-    m_prev = m;
-    ctx->last_cur = cur;
-    h *= 2;
-  }
-
-  // ---- final: fused BWT emission + pidx + LFpowers (+ hole fill)
-  {
-    if (bs)
-      k_finish_batch<<<bs->nblocks, 256, 0, st>>>(ctx->d_rank, N, bstride, bs->nblocks, d_dst, ctx->d_LF, bs->nLF, bs->nLF_last,
-                                                  ctx->d_LF + LF_PARK);
-    else
-      k_finish<<<1, 256, 0, st>>>(ctx->d_rank, d_text, N, d_dst, block_mode ? 1 : 0, ctx->d_LF, nLF, ctx->d_LF + LF_PARK);
+    h_next = std::min<uint64_t>((uint64_t)h32 * 2, 0x7FFFFFFFull);
+    k_commit_sort<<<1, 1, 0, st>>>(ctx->d_state, ctx->d_ctrl(), (uint32_t)h_next, sel_of(cur), expect_cursor);
     CK(ctx, cudaGetLastError());
     S.kernel_launches++;
-    S.algorithmic_bytes += (uint64_t)N * 2;  // text gather + BWT byte, charged once per suffix (done inside k_rerank)
-  }
-  CK(ctx, cudaEventRecord(ctx->ev_end, st));
-  CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_LF + LF_WATCH, 4, cudaMemcpyDeviceToHost, st));
-  if (bs) {
-    CK(ctx, cudaMemcpyAsync(h_bLF, ctx->d_LF, (size_t)bs->nblocks * 256 * 4, cudaMemcpyDeviceToHost, st));
-    for (uint32_t k = 0; k < bs->nblocks; ++k) {  // block k's BWT bytes are out[k*stride .. k*stride + n_k)
-      const uint32_t nk = (k + 1 == bs->nblocks) ? bs->n_last : bs->n0;
-      CK(ctx, cudaMemcpyAsync(bs->out[k], ctx->d_out + (size_t)k * bstride, nk,
-                              bs->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (r < BWTC_CUDA_MAX_ROUNDS) {
+      S.live[r] = m;
+      S.passes[r] = pdone;
+      S.prefix_len[r] = h32;
+      S.rounds = r + 1;
     }
-  } else {
-    CK(ctx, cudaMemcpyAsync(ctx->h_LF(), ctx->d_LF, nLF * 4, cudaMemcpyDeviceToHost, st));
-    if (!out_dev) CK(ctx, cudaMemcpyAsync(h_out, ctx->d_out, n, cudaMemcpyDeviceToHost, st));
+    m_prev = m;
+    ctx->last_cur = cur;
+    lists_pending = true;
   }
-  CK(ctx, cudaStreamSynchronize(st));
-  if (ctx->h_ctrl()[0]) {
-    set_err(ctx->err, "tail refinement kernel did not converge (code %u)", ctx->h_ctrl()[0]);
-    return BWTC_CUDA_EINTERNAL;
+
+  // ---- result copies that could not be enqueued speculatively
+  if (finished) {
+    if (bs) {
+      if (!out_enqueued || !direct_out) {
+        if (direct_out) {
+          if (enqueue_direct_out() || host_wait(ctx, st)) return BWTC_CUDA_ECUDA;
+        } else {
+          for (uint32_t k = 0; k < bs->nblocks; ++k) {
+            const uint32_t nk = (k + 1 == bs->nblocks) ? bs->n_last : bs->n0;
+            if (download_staged(ctx, static_cast<uint8_t*>(bs->out[k]), ctx->d_out + (size_t)k * J.bstride, nk)) return BWTC_CUDA_ECUDA;
+          }
+        }
+      }
+    } else if (!J.out_dev) {
+      if (!J.block_mode) {
+        // raw contract: U[pidx] stays untouched (divsufsort.c:506-512) — two ranges around it
+        const uint32_t pidx = ctx->h_LF()[0];
+        if (is_pinned_host(J.h_out)) {
+          if (pidx > 0) CK(ctx, cudaMemcpyAsync(J.h_out, ctx->d_out, pidx, cudaMemcpyDeviceToHost, st));
+          if (pidx + 1 < n) CK(ctx, cudaMemcpyAsync(J.h_out + pidx + 1, ctx->d_out + pidx + 1, n - pidx - 1, cudaMemcpyDeviceToHost, st));
+          if (host_wait(ctx, st)) return BWTC_CUDA_ECUDA;
+        } else {
+          if (download_staged(ctx, J.h_out, ctx->d_out, pidx)) return BWTC_CUDA_ECUDA;
+          if (pidx + 1 < n && download_staged(ctx, J.h_out + pidx + 1, ctx->d_out + pidx + 1, n - pidx - 1)) return BWTC_CUDA_ECUDA;
+        }
+      } else if (!out_enqueued) {
+        if (direct_out) {
+          if (enqueue_direct_out() || host_wait(ctx, st)) return BWTC_CUDA_ECUDA;
+        } else if (download_staged(ctx, J.h_out, ctx->d_out, n)) {
+          return BWTC_CUDA_ECUDA;
+        }
+      }
+    }
   }
+  // ---- results for the caller: LFpowers, freqs (incremented only now that the block has succeeded)
   if (bs) {
+    const uint32_t* h_bhist = reinterpret_cast<const uint32_t*>(ctx->h_batch + MAX_BATCH * sizeof(void*));
     for (uint32_t k = 0; k < bs->nblocks; ++k) {
       const uint32_t nl = (k + 1 == bs->nblocks) ? bs->nLF_last : bs->nLF;
-      for (uint32_t j = 0; j < nl; ++j) LF[k * 256 + j] = h_bLF[k * 256 + j];
+      for (uint32_t j = 0; j < nl; ++j) J.LF[k * 256 + j] = h_bLF[k * 256 + j];
+      if (J.freqs)
+        for (int c = 0; c < 256; ++c) J.freqs[k * 256 + c] += h_bhist[k * 256 + c];
     }
   } else {
-    for (uint32_t j = 0; j < nLF; ++j) LF[j] = ctx->h_LF()[j];
+    for (uint32_t j = 0; j < J.nLF; ++j) J.LF[j] = ctx->h_LF()[j];
+    if (J.freqs)
+      for (int c = 0; c < 256; ++c) J.freqs[c] += ctx->h_hist()[c];
   }
   float ms = 0;
   CK(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
@@ -844,39 +1094,33 @@ int64_t run_transform_once(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h
     S.sort_ms = tot;
     S.sort0_ms = tot0;
   }
-  return (int64_t)LF[0];
+  return (int64_t)J.LF[0];
 }
 
-// run_transform_once + the fallback of the static tile ids (see k_radix_pass): if the look-back watchdog fired, the
-// context switches to ticket counters for good and — when the caller's input is still intact — repeats the call.
+// Phase A, phase B, and the fallback of the static tile ids (see k_radix_pass): if the look-back watchdog fired, the
+// context switches to ticket counters for good and repeats phase B.  The reversed, sentinel-terminated text is still
+// intact on the device, so this works for in-place device buffers too; nothing was written to LFpowers / freqs.
 int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, uint8_t* h_out, const uint8_t* in_dev,
                       uint8_t* out_dev, uint32_t n, uint32_t* LF, uint32_t nLF, uint32_t* freqs,
                       const BatchSpec* bs = nullptr) {
-  // freqs are incremented before any look-back kernel runs: hand the first attempt a scratch copy
-  std::vector<uint32_t> fr_tmp;
-  uint32_t* fr = freqs;
-  BatchSpec b2;
-  if (freqs && ctx->static_tiles) {
-    fr_tmp.assign((size_t)256 * (bs ? bs->nblocks : 1u), 0u);
-    fr = fr_tmp.data();
-    if (bs) { b2 = *bs; b2.freqs = fr; }
-  }
-  const bool scratch = (fr != freqs);
-  int64_t rc = run_transform_once(ctx, block_mode, h_in, h_out, in_dev, out_dev, n, LF, nLF, fr, (bs && scratch) ? &b2 : bs);
+  Job J;
+  J.block_mode = block_mode;
+  J.h_in = h_in;
+  J.h_out = h_out;
+  J.in_dev = in_dev;
+  J.out_dev = out_dev;
+  J.n = n;
+  J.LF = LF;
+  J.nLF = nLF;
+  J.freqs = freqs;
+  J.bs = bs;
+  int64_t rc = phase_input(ctx, J);
+  if (rc < 0) return rc;
+  rc = phase_sort(ctx, J);
   if (rc == BWTC_CUDA_EINTERNAL && ctx->lb_watchdog && ctx->static_tiles) {
     ctx->static_tiles = 0;
-    bool intact = bs ? !bs->on_device : (in_dev == nullptr || in_dev != out_dev);
-    if (bs && bs->on_device) {
-      intact = true;
-      for (uint32_t k = 0; k < bs->nblocks; ++k) intact = intact && (bs->in[k] != bs->out[k]);
-    }
-    if (intact) {
-      if (scratch) std::fill(fr_tmp.begin(), fr_tmp.end(), 0u);
-      rc = run_transform_once(ctx, block_mode, h_in, h_out, in_dev, out_dev, n, LF, nLF, fr, (bs && scratch) ? &b2 : bs);
-    }
+    rc = phase_sort(ctx, J);
   }
-  if (scratch && rc >= 0)
-    for (size_t i = 0; i < fr_tmp.size(); ++i) freqs[i] += fr_tmp[i];
   return rc;
 }
 
@@ -915,6 +1159,7 @@ int transform_batch(bwtc_cuda_ctx* ctx, const void* const* in, void* const* out,
     bs.freqs = freqs;
     const int64_t rc = run_transform(ctx, true, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, &bs);
     if (rc != BATCH_NEEDS_SINGLE) {
+      ctx->stats.batch_blocks = count;  // the record describes the whole batch: count it once, not per block
       if (stats) for (uint32_t k = 0; k < count; ++k) stats[k] = ctx->stats;
       return rc < 0 ? (int)rc : 0;
     }
@@ -928,6 +1173,7 @@ int transform_batch(bwtc_cuda_ctx* ctx, const void* const* in, void* const* out,
     else
       rc = run_transform(ctx, true, static_cast<const uint8_t*>(in[k]), static_cast<uint8_t*>(out[k]), nullptr, nullptr, sizes[k],
                          LF + (size_t)k * 256, nLF[k], fr);
+    ctx->stats.batch_blocks = 1;
     if (stats) stats[k] = ctx->stats;
     if (rc < 0) return (int)rc;
   }
@@ -974,6 +1220,13 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   c->cap = max_block_bytes;
   if (const char* e = getenv("BWTC_STATIC_TILES")) c->static_tiles = atoi(e);
   if (const char* e = getenv("BWTC_DEBUG_FAKE_WATCHDOG")) c->debug_fake_watchdog = atoi(e);
+  if (const char* e = getenv("BWTC_DEBUG_REVERSE_TILES")) c->debug_reverse_tiles = atoi(e);
+  if (const char* e = getenv("BWTC_SPIN_WAIT")) c->wait_mode = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("BWTC_WAIT_MODE")) c->wait_mode = atoi(e);
+  if (const char* e = getenv("BWTC_POLL_SPIN_US")) c->poll_spin_us = std::max(0, atoi(e));
+  if (const char* e = getenv("BWTC_POLL_SLEEP_US")) c->poll_sleep_us = std::max(1, atoi(e));
+  if (const char* e = getenv("BWTC_LADDER_FIRST")) c->ladder_first = std::max(0, atoi(e));
+  if (const char* e = getenv("BWTC_LADDER_MORE")) c->ladder_more = std::max(1, atoi(e));
   if (const char* e = getenv("BWTC_SEG")) c->use_seg = atoi(e);
   if (const char* e = getenv("BWTC_BATCH")) c->use_batch = atoi(e);
   if (const char* e = getenv("BWTC_PACK_PRED")) c->use_pack_pred = atoi(e);
@@ -1013,6 +1266,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_zero, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)MAX_RERANK_WINDOWS * c->max_aux_tiles * 8 + 64);
   ALLOC(c->d_status, (size_t)MAX_PASSES * (c->max_rs_tiles + LB_PAD_ROWS) * 1024u);
   ALLOC(c->d_LF, (size_t)LF_WORDS * 4);
+  ALLOC(c->d_state, sizeof(LadderState));
   ALLOC(c->d_bhist, (size_t)MAX_BATCH * 256 * 4);
   ALLOC(c->d_bptr, (size_t)MAX_BATCH * sizeof(void*));
   ALLOC(c->d_wtab, (size_t)WS_SLOTS * 12 + 64);
@@ -1032,11 +1286,21 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (!rc) {
     e = cudaMallocHost((void**)&c->h_small, (size_t)(CTR_WORDS + HIST_WORDS + 256 + 8) * 4);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_batch, (size_t)MAX_BATCH * (sizeof(void*) + 2 * 256 * 4));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_state, sizeof(LadderState));
     if (e != cudaSuccess) { set_err(g_err, "cudaMallocHost: %s", cudaGetErrorString(e)); rc = BWTC_CUDA_EALLOC; }
   }
-  if (!rc && (cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess)) {
+  if (!rc && (cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess ||
+              cudaEventCreateWithFlags(&c->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess ||
+              cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+              cudaEventCreateWithFlags(&c->ev_comp, cudaEventDisableTiming) != cudaSuccess)) {
     set_err(g_err, "cudaEventCreate failed");
     rc = BWTC_CUDA_ECUDA;
+  }
+  if (!rc) {
+    if (const char* sl = getenv("BWTC_DEBUG_SPIN_LIMIT")) {  // test hook: a watchdog that fires within milliseconds
+      const uint32_t v = (uint32_t)std::max(1L, atol(sl));
+      if (cudaMemcpyToSymbol(g_lb_spin_limit, &v, sizeof(v)) != cudaSuccess) { set_err(g_err, "cudaMemcpyToSymbol failed"); rc = BWTC_CUDA_ECUDA; }
+    }
   }
   if (!rc) {
     int r2 = 0;
@@ -1064,6 +1328,24 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
 }
 
 void bwtc_cuda_ctx_destroy(bwtc_cuda_ctx* ctx) { ctx_free(ctx); }
+
+/* The device allocations of bwtc_cuda_ctx_create, summed (keep in step with its ALLOC list). */
+uint64_t bwtc_cuda_scratch_bytes(uint32_t max_block_bytes) {
+  const uint64_t N = (uint64_t)max_block_bytes + 1;
+  const uint32_t min_tile = RS_TILE64 < RS_TILE32 ? RS_TILE64 : RS_TILE32;
+  const uint64_t rs_tiles = div_up(N, min_tile), aux_tiles = div_up(N, AUX_TILE);
+  const uint64_t padded = ((N + TEXT_PAD + 15) / 16) * 16 + 16;
+  uint64_t b = 5 * padded;                                  // d_in, d_text, d_out, d_aux[2]
+  b += (N + 64) * 4;                                        // d_rank
+  b += 2 * N * 8 + 2 * N * 4;                               // d_keys[2], d_idx[2]
+  b += N * 4 + 64;                                          // d_scat
+  b += (uint64_t)(CTR_WORDS + HIST_WORDS) * 4 + (uint64_t)MAX_RERANK_WINDOWS * aux_tiles * 8 + 64;  // d_zero
+  b += (uint64_t)MAX_PASSES * (rs_tiles + LB_PAD_ROWS) * 1024u;                                       // d_status
+  b += (uint64_t)LF_WORDS * 4 + sizeof(LadderState) + (uint64_t)MAX_BATCH * 256 * 4 + (uint64_t)MAX_BATCH * sizeof(void*);
+  b += (uint64_t)WS_SLOTS * 12 + 64;                        // d_wtab
+  b += aux_tiles * (2 + MAX_RERANK_WINDOWS + 1) * 4 + 64;   // d_tilecnt
+  return b;
+}
 
 const char* bwtc_cuda_last_error(const bwtc_cuda_ctx* ctx) { return ctx ? ctx->err : g_err; }
 
@@ -1182,10 +1464,28 @@ uint32_t bwtc_cuda_num_starting_points(uint32_t block_bytes, uint32_t starts) {
 }  // extern "C"
 
 // =====================================================================================================
-// Batched pipeline: `depth` contexts on one GPU, one host worker per context, blocks handed out in order.
-// Replaces the synchronous per-slice loop of Compressor::compress (Compressor.cpp:100-109) for the BWT
-// stage; results are delivered by block index so a caller can entropy-code strictly in file order.
+// Batched look-ahead pipeline: `depth` contexts on one GPU, one persistent host worker per context, a FIFO of
+// submitted blocks.  Replaces the synchronous per-slice loop of Compressor::compress (Compressor.cpp:100-109) for the
+// BWT stage; results are delivered per block (ticket), so a caller can entropy-code strictly in file order while
+// later blocks are still in flight.  Workers sleep on a condition variable when the queue is empty and on blocking-sync
+// events while the GPU works: an idle or waiting pipeline costs no host core.
 // =====================================================================================================
+namespace {
+struct PipeItem {
+  const void* in = nullptr;
+  void* out = nullptr;
+  uint32_t n = 0, starts = 0;
+  bool on_device = false;
+  uint32_t* LF = nullptr;   // 256 words
+  uint32_t* nLF = nullptr;
+  uint32_t* freqs = nullptr;
+  bwtc_cuda_stats* stats = nullptr;
+  uint64_t ticket = 0;
+  int rc = 0;
+  bool done = false;
+};
+}  // namespace
+
 struct bwtc_cuda_pipeline {
   int device = 0;
   std::vector<bwtc_cuda_ctx*> ctxs;
@@ -1194,13 +1494,116 @@ struct bwtc_cuda_pipeline {
   std::vector<cudaEvent_t> ev_done;
   uint32_t batch_max_block = 0;  // blocks up to this size are batched ...
   uint32_t batch_blocks = 1;     // ... this many at most per batch
+  // ---- queue
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  std::deque<std::shared_ptr<PipeItem>> queue;                       // submitted, not yet claimed (FIFO)
+  std::unordered_map<uint64_t, std::shared_ptr<PipeItem>> inflight;  // submitted, not yet waited for
+  uint64_t next_ticket = 1;
+  bool stopping = false;
+  std::vector<std::thread> workers;
   char err[512];
 };
+
+namespace {
+
+void pipeline_worker(bwtc_cuda_pipeline* p, bwtc_cuda_ctx* c) {
+  cudaSetDevice(p->device);
+  std::vector<std::shared_ptr<PipeItem>> grp;
+  std::vector<const void*> in;
+  std::vector<void*> out;
+  std::vector<uint32_t> sizes, nLF, LF, freqs;
+  std::vector<bwtc_cuda_stats> stats;
+  for (;;) {
+    grp.clear();
+    {
+      std::unique_lock<std::mutex> lk(p->mu);
+      p->cv_work.wait(lk, [&] { return p->stopping || !p->queue.empty(); });
+      if (p->queue.empty()) return;  // stopping
+      grp.push_back(p->queue.front());
+      p->queue.pop_front();
+      // consecutive small blocks of equal size (same contract parameters) go to ONE device-side sort
+      if (grp[0]->n <= p->batch_max_block) {
+        sizes.assign(1, grp[0]->n);
+        const uint32_t lim = std::min<uint32_t>(MAX_BATCH, p->batch_blocks);
+        while (!p->queue.empty() && grp.size() < lim) {
+          const PipeItem& nx = *p->queue.front();
+          if (nx.starts != grp[0]->starts || nx.on_device != grp[0]->on_device || (nx.freqs == nullptr) != (grp[0]->freqs == nullptr)) break;
+          sizes.push_back(nx.n);
+          if (!batchable(c, sizes.data(), (uint32_t)sizes.size())) { sizes.pop_back(); break; }
+          grp.push_back(p->queue.front());
+          p->queue.pop_front();
+        }
+      }
+    }
+    const uint32_t cnt = (uint32_t)grp.size();
+    int rc;
+    if (cnt == 1) {
+      PipeItem& it = *grp[0];
+      const void* i1 = it.in;
+      void* o1 = it.out;
+      rc = transform_batch(c, &i1, &o1, &it.n, 1, it.starts, it.on_device, it.LF, it.nLF, it.freqs, it.stats);
+    } else {
+      in.resize(cnt); out.resize(cnt); sizes.resize(cnt); nLF.resize(cnt);
+      LF.assign((size_t)cnt * 256, 0u);
+      const bool want_freqs = grp[0]->freqs != nullptr;
+      if (want_freqs) freqs.assign((size_t)cnt * 256, 0u);
+      stats.resize(cnt);
+      for (uint32_t k = 0; k < cnt; ++k) { in[k] = grp[k]->in; out[k] = grp[k]->out; sizes[k] = grp[k]->n; }
+      rc = transform_batch(c, in.data(), out.data(), sizes.data(), cnt, grp[0]->starts, grp[0]->on_device, LF.data(), nLF.data(),
+                           want_freqs ? freqs.data() : nullptr, stats.data());
+      if (rc >= 0)
+        for (uint32_t k = 0; k < cnt; ++k) {
+          PipeItem& it = *grp[k];
+          *it.nLF = nLF[k];
+          for (uint32_t j = 0; j < nLF[k]; ++j) it.LF[j] = LF[(size_t)k * 256 + j];
+          if (want_freqs) for (int ch = 0; ch < 256; ++ch) it.freqs[ch] += freqs[(size_t)k * 256 + ch];
+          if (it.stats) *it.stats = stats[k];
+        }
+    }
+    {
+      std::lock_guard<std::mutex> lk(p->mu);
+      if (rc < 0 && !p->err[0]) set_err(p->err, "block ticket %llu (+%u): %s", (unsigned long long)grp[0]->ticket, cnt - 1, c->err);
+      for (auto& it : grp) { it->rc = rc < 0 ? rc : 0; it->done = true; }
+    }
+    p->cv_done.notify_all();
+  }
+}
+
+uint64_t pipeline_enqueue_locked(bwtc_cuda_pipeline* p, const void* in, void* out, uint32_t n, uint32_t starts, bool on_device,
+                                 uint32_t* LF, uint32_t* nLF, uint32_t* freqs, bwtc_cuda_stats* stats) {
+  auto it = std::make_shared<PipeItem>();
+  it->in = in; it->out = out; it->n = n; it->starts = starts; it->on_device = on_device;
+  it->LF = LF; it->nLF = nLF; it->freqs = freqs; it->stats = stats;
+  it->ticket = p->next_ticket++;
+  p->queue.push_back(it);
+  p->inflight[it->ticket] = it;
+  return it->ticket;
+}
+
+int pipeline_wait_ticket(bwtc_cuda_pipeline* p, uint64_t ticket) {
+  std::unique_lock<std::mutex> lk(p->mu);
+  auto f = p->inflight.find(ticket);
+  if (f == p->inflight.end()) { set_err(p->err, "unknown ticket %llu", (unsigned long long)ticket); return BWTC_CUDA_EARG; }
+  std::shared_ptr<PipeItem> it = f->second;
+  p->cv_done.wait(lk, [&] { return it->done; });
+  p->inflight.erase(ticket);
+  return it->rc;
+}
+
+}  // namespace
 
 extern "C" {
 
 void bwtc_cuda_pipeline_destroy(bwtc_cuda_pipeline* p) {
   if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->stopping = true;
+    p->queue.clear();
+  }
+  p->cv_work.notify_all();
+  for (std::thread& t : p->workers) t.join();
   cudaSetDevice(p->device);
   for (bwtc_cuda_ctx* c : p->ctxs) ctx_free(c);
   for (cudaEvent_t e : p->ev_done) cudaEventDestroy(e);
@@ -1239,10 +1642,11 @@ int bwtc_cuda_pipeline_create(bwtc_cuda_pipeline** out, int device, int depth, u
     p->ctxs.push_back(c);
   }
   bool ok = cudaStreamCreateWithFlags(&p->tstream, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaEventCreate(&p->ev0) == cudaSuccess && cudaEventCreate(&p->ev1) == cudaSuccess;
+            cudaEventCreate(&p->ev0) == cudaSuccess && cudaEventCreateWithFlags(&p->ev1, cudaEventBlockingSync) == cudaSuccess;
   p->ev_done.resize(depth, nullptr);
   for (int i = 0; ok && i < depth; ++i) ok = cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { set_err(g_err, "pipeline stream/event creation failed"); bwtc_cuda_pipeline_destroy(p); return BWTC_CUDA_ECUDA; }
+  for (bwtc_cuda_ctx* c : p->ctxs) p->workers.emplace_back(pipeline_worker, p, c);
   *out = p;
   return 0;
 }
@@ -1267,48 +1671,45 @@ int bwtc_cuda_pipeline_set_timing(bwtc_cuda_pipeline* p, int detail) {
   return 0;
 }
 
+int bwtc_cuda_pipeline_submit(bwtc_cuda_pipeline* p, const uint8_t* in, uint8_t* out, uint32_t n, uint32_t starts,
+                              int on_device, uint32_t* LFpowers, uint32_t* nLF, uint32_t* freqs, bwtc_cuda_stats* stats,
+                              uint64_t* ticket) {
+  if (!p || !in || !out || !LFpowers || !nLF || !ticket || n == 0) { if (p) set_err(p->err, "bad arguments"); return BWTC_CUDA_EARG; }
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    *ticket = pipeline_enqueue_locked(p, in, out, n, starts, on_device != 0, LFpowers, nLF, freqs, stats);
+  }
+  p->cv_work.notify_one();
+  return 0;
+}
+
+int bwtc_cuda_pipeline_wait(bwtc_cuda_pipeline* p, uint64_t ticket) {
+  if (!p) return BWTC_CUDA_EARG;
+  return pipeline_wait_ticket(p, ticket);
+}
+
 int bwtc_cuda_pipeline_run(bwtc_cuda_pipeline* p, const uint8_t* const* in, uint8_t* const* out, const uint32_t* sizes,
                            uint32_t nblocks, uint32_t starts, int on_device, uint32_t* LFpowers, uint32_t* nLF,
                            uint32_t* freqs, bwtc_cuda_stats* stats) {
   if (!p || !in || !out || !sizes || !LFpowers || !nLF) { if (p) set_err(p->err, "bad arguments"); return BWTC_CUDA_EARG; }
-  p->err[0] = 0;
-  // Consecutive small blocks of equal size are grouped and handed to a worker as one batch (one device-side
-  // sorting problem, see transform_batch); everything else is one block per claim.
-  std::vector<uint32_t> gstart;
-  for (uint32_t i = 0; i < nblocks;) {
-    uint32_t j = i + 1;
-    if (sizes[i] <= p->batch_max_block) {
-      const uint32_t lim = std::min<uint32_t>(nblocks, i + std::min<uint32_t>(MAX_BATCH, p->batch_blocks));
-      while (j < lim && batchable(p->ctxs[0], sizes + i, j + 1 - i)) ++j;
-    }
-    gstart.push_back(i);
-    i = j;
+  for (uint32_t i = 0; i < nblocks; ++i)
+    if (!in[i] || !out[i] || sizes[i] == 0) { set_err(p->err, "null or empty block %u", i); return BWTC_CUDA_EARG; }
+  std::vector<uint64_t> tickets(nblocks);
+  {
+    // all blocks are queued before any worker wakes up, so runs of small blocks are grouped deterministically
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->err[0] = 0;
+    for (uint32_t i = 0; i < nblocks; ++i)
+      tickets[i] = pipeline_enqueue_locked(p, in[i], out[i], sizes[i], starts, on_device != 0, LFpowers + (size_t)i * 256, nLF + i,
+                                           freqs ? freqs + (size_t)i * 256 : nullptr, stats ? stats + i : nullptr);
   }
-  gstart.push_back(nblocks);
-  const uint32_t ngroups = (uint32_t)gstart.size() - 1;
-  std::atomic<uint32_t> next(0);
-  std::atomic<int> first_err(0);
-  std::mutex err_mu;
-  auto worker = [&](bwtc_cuda_ctx* c) {
-    for (;;) {
-      const uint32_t g = next.fetch_add(1);
-      if (g >= ngroups || first_err.load()) break;
-      const uint32_t i = gstart[g], cnt = gstart[g + 1] - i;
-      const int rc = transform_batch(c, reinterpret_cast<const void* const*>(in + i), reinterpret_cast<void* const*>(out + i),
-                                     sizes + i, cnt, starts, on_device != 0, LFpowers + (size_t)i * 256, nLF + i,
-                                     freqs ? freqs + (size_t)i * 256 : nullptr, stats ? stats + i : nullptr);
-      if (rc < 0) {
-        std::lock_guard<std::mutex> gl(err_mu);
-        if (!first_err.load()) { first_err.store(rc); set_err(p->err, "blocks %u..%u: %s", i, i + cnt - 1, c->err); }
-        break;
-      }
-    }
-  };
-  std::vector<std::thread> threads;
-  for (size_t t = 1; t < p->ctxs.size(); ++t) threads.emplace_back(worker, p->ctxs[t]);
-  worker(p->ctxs[0]);
-  for (std::thread& t : threads) t.join();
-  return first_err.load();
+  p->cv_work.notify_all();
+  int first_err = 0;
+  for (uint32_t i = 0; i < nblocks; ++i) {
+    const int rc = pipeline_wait_ticket(p, tickets[i]);
+    if (rc < 0 && !first_err) first_err = rc;
+  }
+  return first_err;
 }
 
 int bwtc_cuda_pipeline_timing_begin(bwtc_cuda_pipeline* p) {

@@ -29,21 +29,28 @@ namespace bwtc_b200 {
 constexpr uint32_t RANK_DONE = 0x80000000u;  // bit 31 of rank[i]: suffix i is alone in its group (final)
 constexpr uint32_t RANK_MASK = 0x7FFFFFFFu;
 
-// ---- control words (one uint32 array per context, zeroed by a memset at the start of every round)
-constexpr int CTR_PASS0 = 0;       // [0..15]  tile ticket counters of the radix passes (watchdog-fallback mode only)
-constexpr uint32_t CTR_STATIC = 0xFFFFFFFFu;  // "no ticket counter: tile id = blockIdx.x"
-constexpr int CTR_RERANK = 32;     // [32..47] tile ticket counters of the k_rerank window launches (fallback mode only)
+// ---- control words (one uint32 array per context).  Words [0, CTR_STICKY) are zeroed once per block, the others by
+//      a memset at the start of every sort round.
+constexpr int CTR_ERR = 0;         // != 0: a look-back watchdog fired / an internal check failed.  STICKY: every later
+                                   // kernel of the block returns at entry, so nothing consumes half-written buffers
+constexpr int CTR_STICKY = 8;
+constexpr int CTR_PASS0 = 8;       // [8..23]  tile ticket counters of the radix passes (ticket mode only)
+constexpr uint32_t CTR_STATIC = 0xFFFFFFFFu;      // "no ticket counter: tile id = blockIdx.x"
+constexpr uint32_t CTR_STATIC_REV = 0xFFFFFFFEu;  // test hook: tile id = gridDim.x - 1 - blockIdx.x (a dispatch order
+                                                  // that is as wrong as it can be; see tests/test_gpu_parity.py)
+constexpr int CTR_CURSOR = 24;     // output cursor of k_build_keys (== number of live records emitted)
+constexpr int CTR_LIVE = 25;       // records still in non-singleton groups after the re-rank of this round
+constexpr int CTR_MAXGROUP = 26;   // size of the largest non-singleton group seen by the re-rank of this round
+constexpr int CTR_UPD = 27;        // cursor of the rank-update list written by k_seg_round
+constexpr int CTR_RERANK = 32;     // [32..47] tile ticket counters of the k_rerank window launches (ticket mode only)
 constexpr int MAX_RERANK_WINDOWS = 16;
-constexpr int CTR_CURSOR = 17;     // output cursor of k_build_keys (== number of live records emitted)
-constexpr int CTR_LIVE = 18;       // records still in non-singleton groups after k_rerank
-constexpr int CTR_UPD = 21;        // cursor of the rank-update list written by k_seg_round
-constexpr int CTR_MAXGROUP = 20;   // size of the largest non-singleton group seen by the re-rank of this round
-constexpr int CTR_ERR = 19;        // != 0: a look-back watchdog fired (engine returns BWTC_CUDA_EINTERNAL)
 constexpr int CTR_WORDS = 64;
 
 // look-back status words of the radix pass: 2 flag bits + 30-bit count
 constexpr uint32_t LB_AGG = 0x40000000u, LB_PREFIX = 0x80000000u, LB_VALUE = 0x3FFFFFFFu;
-constexpr uint32_t LB_SPIN_LIMIT = 1u << 24;
+// Spin watchdog of the look-back loops (a violated dispatch-order assumption becomes an error, not a hang).
+// __constant__ so a test can shrink it (BWTC_DEBUG_SPIN_LIMIT, read by bwtc_cuda_ctx_create).
+__constant__ uint32_t g_lb_spin_limit = 1u << 24;
 constexpr int LB_PAD_ROWS = 8;  // rows of "prefix 0" in front of tile 0 (>= LB_BATCH): look-back loads need no bounds check
 #ifndef BWTC_LB_BATCH
 #define BWTC_LB_BATCH 8
@@ -473,6 +480,7 @@ __global__ void __launch_bounds__(256) k_build_keys(const uint32_t* __restrict__
   __shared__ uint32_t s_wtot[WARPS];
   __shared__ uint32_t s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (ld_relaxed_u32(ctrl + CTR_ERR)) return;
 #pragma unroll
   for (int p = 0; p < 8; ++p) s_hist[p * 256 + tid] = 0;
   __syncthreads();
@@ -613,11 +621,18 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(KeyT) == 4 && !AUX) ? BWTC_RS_M
   // watchdog turns a violation into an error, and the host then repeats the block with tickets (ctr_slot = a
   // zeroed ctrl word), which are safe under any dispatch order.
   uint32_t tile = blockIdx.x;
-  if (ctr_slot != CTR_STATIC) {
+  if (ctr_slot == CTR_STATIC_REV) {
+    tile = gridDim.x - 1u - blockIdx.x;
+  } else if (ctr_slot != CTR_STATIC) {
     if (tid == 0) s_misc[0] = atomicAdd(&ctrl[ctr_slot], 1u);
     __syncthreads();
     tile = s_misc[0];
   }
+  // Sticky error word: once a watchdog has fired anywhere in this block's kernel sequence, every later CTA returns
+  // before it touches a buffer (the load is issued here, next to the record loads, and tested behind them).
+  // (a plain load, not an asm volatile one: it must not fence the record loads below; kernel boundaries make the word
+  // visible, and a CTA that misses a concurrent failure merely finishes its tile)
+  const uint32_t err_at_entry = ctrl[CTR_ERR];
   // (the per-warp histograms are zeroed AFTER the loads have been issued: their latency covers the zeroing and
   // the barrier)
 #ifdef BWTC_PROFILE_STAGES
@@ -674,6 +689,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(KeyT) == 4 && !AUX) ? BWTC_RS_M
     }
   }
 
+  if (err_at_entry) return;
   for (int i = lane; i < 256; i += 32) s_whist[warp * 256 + i] = 0;  // each warp zeroes (and then ranks into) its own
   __syncwarp();
 #ifdef BWTC_PROFILE_STAGES
@@ -774,8 +790,9 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(KeyT) == 4 && !AUX) ? BWTC_RS_M
         done = fin != 0;
         t -= consumed;
         if (!done && consumed == 0) {
-          if (++spins > LB_SPIN_LIMIT) {
-            atomicExch(&ctrl[CTR_ERR], 1u);
+          ++spins;
+          if (spins > g_lb_spin_limit || ((spins & 255u) == 0u && ld_relaxed_u32(ctrl + CTR_ERR))) {
+            atomicExch(&ctrl[CTR_ERR], 1u);  // (or somebody else's watchdog fired: stop waiting for a tile that gave up)
             break;
           }
           __nanosleep(20);
@@ -915,11 +932,14 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
   uint32_t tile = blockIdx.x;
   if (ROUND0 && rp.packed) s_dec[tid] = rp.decode[tid];
   if (tid <= MAX_RERANK_WINDOWS) s_bcnt[tid] = 0;
-  if (rp.ctr_slot != CTR_STATIC) {
+  if (rp.ctr_slot == CTR_STATIC_REV) {
+    tile = gridDim.x - 1u - blockIdx.x;
+  } else if (rp.ctr_slot != CTR_STATIC) {
     if (tid == 0) s_tile = atomicAdd(&ctrl[rp.ctr_slot], 1u);
     __syncthreads();
     tile = s_tile;
   }
+  if (ld_relaxed_u32(ctrl + CTR_ERR)) return;  // sticky: an earlier kernel of this block failed (see k_radix_pass)
   const uint32_t m = rp.m;
   const uint32_t tile_base = tile * (uint32_t)TILE;
   if (tile_base >= m) return;
@@ -1076,7 +1096,8 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
         const long long t = base - lane;
         unsigned long long v = (t >= 0) ? ld_relaxed_u64(tstate + t) : ((2ull << 62) | (2ull << 30));  // before tile 0
         while ((v >> 62) == 0ull) {                                             // not published yet
-          if (++spins > LB_SPIN_LIMIT) {
+          ++spins;
+          if (spins > g_lb_spin_limit || ((spins & 255u) == 0u && ld_relaxed_u32(ctrl + CTR_ERR))) {
             atomicExch(&ctrl[CTR_ERR], 2u);
             v = (2ull << 62) | (2ull << 30);
             break;
@@ -1236,7 +1257,8 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
 __global__ void __launch_bounds__(256) k_scatter_bucket(const uint32_t* __restrict__ sc_id, const uint32_t* __restrict__ sc_nr,
                                                         const uint32_t* __restrict__ tile_woff, uint32_t ntiles,
                                                         uint32_t nbuckets, uint32_t b, uint32_t tile_records,
-                                                        uint32_t* __restrict__ rank) {
+                                                        uint32_t* __restrict__ rank, const uint32_t* __restrict__ ctrl) {
+  if (ld_relaxed_u32(ctrl + CTR_ERR)) return;  // sticky error: the staged pairs may be incomplete
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t nw = gridDim.x * (blockDim.x >> 5);
   for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < ntiles; tile += nw) {
@@ -1246,6 +1268,83 @@ __global__ void __launch_bounds__(256) k_scatter_bucket(const uint32_t* __restri
 #pragma unroll 4
     for (uint32_t t = lo + lane; t < hi; t += 32) rank[__ldcs(sc_id + base + t)] = __ldcs(sc_nr + base + t);
   }
+}
+
+// =====================================================================================================
+// Device-side round control ("ladder").  After a sort round (round 0 or a global radix round) the host does NOT
+// read the live count back to decide what comes next: it enqueues the whole remaining sequence — live lists,
+// a few segmented rounds, the single-CTA tail, k_finish, the result copies — and every kernel decides from this
+// device-resident state whether it has work (k_commit_* update it between the kernels).  A block whose later rounds
+// are all sort-free therefore needs ONE host synchronisation after round 0 instead of one per round; only when the
+// ladder ends with suffixes still live (large groups: a global radix round is needed, or more segmented rounds than
+// were enqueued) does the host step in again with the state it reads back.
+// =====================================================================================================
+constexpr int LADDER_LOG = 40;  // == BWTC_CUDA_MAX_ROUNDS
+constexpr int SEG_T = 1920, SEG_CAP = 2048, SEG_MAXGROUP = 128;
+constexpr int SMALL_MAX = 2048;
+struct LadderState {
+  uint32_t m;         // live records (suffixes in non-singleton groups)
+  uint32_t maxgroup;  // largest group among them
+  uint32_t h;         // prefix length every group agrees on (doubles per round, capped at 0x7FFFFFFF)
+  uint32_t sel;       // pool indices of the rank-ordered (rank, id) lists of the live records: nr | id << 4
+  uint32_t nlog;      // rounds logged below
+  uint32_t lists;     // != 0: the lists at `sel` are valid
+  uint32_t err;       // copy of ctrl[CTR_ERR] taken by k_finish (so one D2H brings everything back)
+  uint32_t pad;
+  uint32_t log_m[LADDER_LOG];     // records processed by ladder round i
+  uint32_t log_kind[LADDER_LOG];  // 1 = segmented round, 2 = tail (k_small_rounds: all remaining rounds)
+  uint32_t log_h[LADDER_LOG];
+};
+// The six u32[N] work arrays (halves of the two key buffers, the two id buffers) the lists rotate through.
+struct PoolPtrs { uint32_t* p[6]; };
+
+__device__ __forceinline__ bool ladder_wants_seg(const LadderState& st) {
+  return st.lists && st.m > (uint32_t)SMALL_MAX && st.maxgroup <= (uint32_t)SEG_MAXGROUP;
+}
+__device__ __forceinline__ bool ladder_wants_lists(uint32_t m, uint32_t maxgroup) {
+  return m != 0u && (m <= (uint32_t)SMALL_MAX || maxgroup <= (uint32_t)SEG_MAXGROUP);
+}
+// out_nr, out_id, upd_a, upd_b = the four pool arrays not holding the current lists, in index order
+__device__ __forceinline__ void ladder_free_slots(uint32_t sel, int* f) {
+  const int a = (int)(sel & 15u), b = (int)(sel >> 4);
+  int nf = 0;
+#pragma unroll
+  for (int q = 0; q < 6; ++q)
+    if (q != a && q != b && nf < 4) f[nf++] = q;
+}
+
+// After a sort round: take the re-rank's totals, name the place the lists WILL be in (k_gather_chunks builds them
+// only if the next step consumes them), clear the accumulators for the segmented rounds.
+__global__ void k_commit_sort(LadderState* st, uint32_t* ctrl, uint32_t h_new, uint32_t sel_lists, uint32_t expect_cursor) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // k_build_keys must have emitted exactly the records the previous round left live (0xFFFFFFFF: no such check)
+  if (expect_cursor != 0xFFFFFFFFu && ctrl[CTR_CURSOR] != expect_cursor && !ctrl[CTR_ERR]) ctrl[CTR_ERR] = 5u;
+  const uint32_t m = ctrl[CTR_LIVE], g = ctrl[CTR_MAXGROUP];
+  st->m = m;
+  st->maxgroup = g;
+  st->h = h_new;
+  st->sel = sel_lists;
+  st->lists = ladder_wants_lists(m, g) ? 1u : 0u;
+  ctrl[CTR_LIVE] = 0;
+  ctrl[CTR_MAXGROUP] = 0;
+  ctrl[CTR_UPD] = 0;
+}
+
+// After k_seg_round + k_apply_ranks.
+__global__ void k_commit_seg(LadderState* st, uint32_t* ctrl) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (!ladder_wants_seg(*st) || ctrl[CTR_ERR]) return;  // the round did not run
+  const uint32_t i = st->nlog;
+  if (i < (uint32_t)LADDER_LOG) { st->log_m[i] = st->m; st->log_kind[i] = 1u; st->log_h[i] = st->h; st->nlog = i + 1u; }
+  int f[4];
+  ladder_free_slots(st->sel, f);
+  st->sel = (uint32_t)f[0] | ((uint32_t)f[1] << 4);
+  st->m = ctrl[CTR_LIVE];
+  st->maxgroup = ctrl[CTR_MAXGROUP];
+  st->h = st->h >= 0x40000000u ? 0x7FFFFFFFu : st->h * 2u;
+  ctrl[CTR_LIVE] = 0;
+  ctrl[CTR_MAXGROUP] = 0;
+  ctrl[CTR_UPD] = 0;
 }
 
 // k_scan_tile_counts (one CTA): exclusive prefix of the per-tile live counts.  k_gather_chunks: tile t copies its
@@ -1294,7 +1393,11 @@ __global__ void __launch_bounds__(256) k_gather_chunks(const uint32_t* __restric
                                                        const uint32_t* __restrict__ stage_id,
                                                        const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ excl,
                                                        uint32_t tile_records, uint32_t* __restrict__ out_nr,
-                                                       uint32_t* __restrict__ out_id) {
+                                                       uint32_t* __restrict__ out_id,
+                                                       const LadderState* __restrict__ st, const uint32_t* __restrict__ ctrl) {
+  // st != nullptr: speculative launch — only if the next step consumes the lists (k_commit_sort decided)
+  if (st && !st->lists) return;
+  if (ld_relaxed_u32(ctrl + CTR_ERR)) return;
   const uint32_t tile = blockIdx.x;
   const uint32_t c = cnt[tile], dst = excl[tile];
   const size_t src = (size_t)tile * tile_records;
@@ -1313,9 +1416,10 @@ __global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restr
                                                          const uint32_t* __restrict__ rank, uint32_t N, uint32_t h,
                                                          int lo_bits, unsigned long long* __restrict__ keys,
                                                          uint32_t* __restrict__ idx, uint32_t* __restrict__ hist,
-                                                         int npass) {
+                                                         int npass, const uint32_t* __restrict__ ctrl) {
   __shared__ uint32_t s_hist[8 * 256];
   const int tid = threadIdx.x;
+  if (ld_relaxed_u32(ctrl + CTR_ERR)) return;
 #pragma unroll
   for (int p = 0; p < 8; ++p) s_hist[p * 256 + tid] = 0;
   __syncthreads();
@@ -1349,21 +1453,37 @@ __global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restr
 #ifndef BWTC_SEG_MINB
 #define BWTC_SEG_MINB 4
 #endif
-constexpr int SEG_T = 1920, SEG_CAP = 2048, SEG_MAXGROUP = 128;
 
-__global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const uint32_t* __restrict__ nr_in, const uint32_t* __restrict__ id_in,
-                                                   uint32_t m_in, const uint32_t* __restrict__ rank, uint32_t N,
-                                                   uint32_t h, EmitParams ep, uint32_t* __restrict__ nr_out,
-                                                   uint32_t* __restrict__ id_out, uint32_t* __restrict__ upd_id,
-                                                   uint32_t* __restrict__ upd_nr, uint32_t* __restrict__ ctrl) {
+// Persistent grid: tile t = blockIdx.x, blockIdx.x + gridDim.x, ... while t * SEG_T < m (m is read from the
+// device-side LadderState, so the host can enqueue the round before it knows how many suffixes are live).
+__global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const LadderState* __restrict__ st, PoolPtrs pool,
+                                                   const uint32_t* __restrict__ rank, uint32_t N, EmitParams ep,
+                                                   uint32_t* __restrict__ ctrl) {
   constexpr int IPT = SEG_CAP / 256;
   __shared__ unsigned long long s_key[SEG_CAP];
   __shared__ uint32_t s_id[SEG_CAP];
   __shared__ uint32_t s_wa[8], s_wb[8];
   __shared__ uint32_t s_start, s_end, s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t a = blockIdx.x * (uint32_t)SEG_T;
-  if (a >= m_in) return;
+  if (!ladder_wants_seg(*st) || ld_relaxed_u32(ctrl + CTR_ERR)) return;
+  const uint32_t m_in = st->m, h = st->h;
+  // the six list pointers live in shared memory (they would cost 12 registers across the tile loop)
+  __shared__ uint32_t* s_ptr[6];  // [0] nr_in [1] id_in [2] nr_out [3] id_out [4] upd_id [5] upd_nr
+  if (tid == 0) {
+    int fslot[4];
+    ladder_free_slots(st->sel, fslot);
+    s_ptr[0] = pool.p[st->sel & 15u];
+    s_ptr[1] = pool.p[st->sel >> 4];
+    for (int q = 0; q < 4; ++q) s_ptr[2 + q] = pool.p[fslot[q]];
+  }
+#define nr_in (static_cast<const uint32_t*>(s_ptr[0]))
+#define id_in (static_cast<const uint32_t*>(s_ptr[1]))
+#define nr_out (s_ptr[2])
+#define id_out (s_ptr[3])
+#define upd_id (s_ptr[4])
+#define upd_nr (s_ptr[5])
+  for (uint32_t a = blockIdx.x * (uint32_t)SEG_T; a < m_in; a += gridDim.x * (uint32_t)SEG_T) {
+  __syncthreads();  // shared memory of the previous tile is free (first trip: s_ptr is visible)
   const uint32_t b = (m_in - a > (uint32_t)SEG_T) ? a + SEG_T : m_in;
   if (tid == 0) { s_start = 0xFFFFFFFFu; s_end = (b >= m_in) ? m_in : 0xFFFFFFFFu; }
   __syncthreads();
@@ -1387,10 +1507,10 @@ __global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const uint32_t
   __syncthreads();
   const uint32_t start = s_start, end = s_end;
   if (start == 0xFFFFFFFFu || end == 0xFFFFFFFFu || (start < end && end - start > (uint32_t)SEG_CAP)) {
-    if (tid == 0) atomicExch(&ctrl[CTR_ERR], 4u);  // a group longer than SEG_MAXGROUP: the host must not pick this path
-    return;
+    if (tid == 0) atomicExch(&ctrl[CTR_ERR], 4u);  // a group longer than SEG_MAXGROUP: this path must not be picked
+    continue;
   }
-  if (start >= end) return;
+  if (start >= end) continue;
   // ---- load my records (thread-blocked, order preserved), drop the holes, build (old rank, rank[i+h]) keys
   uint32_t myid[IPT], mynr[IPT];
   uint32_t livemask = 0;
@@ -1431,7 +1551,7 @@ __global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const uint32_t
     }
   }
   __syncthreads();
-  if (L == 0) return;
+  if (L == 0) continue;
   const uint32_t P = L;
   // ---- order every group by counting: the records are already grouped by old rank, groups are short
   // (<= SEG_MAXGROUP), so each record just counts the members of its own group that precede it.  No sorting
@@ -1576,12 +1696,24 @@ __global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const uint32_t
       }
     }
   }
+  }  // tile loop
+#undef nr_in
+#undef id_in
+#undef nr_out
+#undef id_out
+#undef upd_id
+#undef upd_nr
 }
 
 // k_apply_ranks — second half of a segmented round: rank[id] = new rank for every record whose rank changed or
 // became final.  The count is read from ctrl[CTR_UPD] on the device (no host round trip in between).
-__global__ void __launch_bounds__(256) k_apply_ranks(const uint32_t* __restrict__ upd_id, const uint32_t* __restrict__ upd_nr,
+__global__ void __launch_bounds__(256) k_apply_ranks(const LadderState* __restrict__ st, PoolPtrs pool,
                                                      const uint32_t* __restrict__ ctrl, uint32_t* __restrict__ rank) {
+  if (!ladder_wants_seg(*st) || ld_relaxed_u32(ctrl + CTR_ERR)) return;  // the round did not run
+  int fslot[4];
+  ladder_free_slots(st->sel, fslot);
+  const uint32_t* __restrict__ upd_id = pool.p[fslot[2]];
+  const uint32_t* __restrict__ upd_nr = pool.p[fslot[3]];
   const uint32_t n = ctrl[CTR_UPD];
   const uint32_t stride = gridDim.x * blockDim.x;
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1599,24 +1731,30 @@ __global__ void __launch_bounds__(256) k_apply_ranks(const uint32_t* __restrict_
 // without returning to the host, instead of ~10 launch-latency-bound kernels per round.
 // Replaces the tail of trsort's loop (trsort.c:563-585), where only a few groups are left.
 // =====================================================================================================
-constexpr int SMALL_MAX = 2048;
-
-__global__ void __launch_bounds__(1024) k_small_rounds(const uint32_t* __restrict__ list, uint32_t m0, uint32_t* rank,
-                                                       uint32_t N, uint32_t h0, EmitParams ep,
-                                                       uint32_t* __restrict__ errflag) {
+__global__ void __launch_bounds__(1024) k_small_rounds(LadderState* st, PoolPtrs pool, uint32_t* rank,
+                                                       uint32_t N, EmitParams ep, uint32_t* __restrict__ ctrl) {
   __shared__ unsigned long long s_key[SMALL_MAX];
   __shared__ uint32_t s_id[SMALL_MAX];
   __shared__ uint32_t s_a[32], s_b[32];
   __shared__ uint32_t s_m;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t m0 = st->m;
+  if (!st->lists || m0 == 0u || m0 > (uint32_t)SMALL_MAX || ld_relaxed_u32(ctrl + CTR_ERR)) return;  // not (yet) the tail
+  const uint32_t* __restrict__ list = pool.p[st->sel >> 4];
   for (int j = tid; j < SMALL_MAX; j += 1024) s_id[j] = (j < (int)m0) ? list[j] : 0u;
   uint32_t m = m0;
-  unsigned long long h = h0;
+  unsigned long long h = st->h;
   uint32_t iters = 0;
-  __syncthreads();
+  __syncthreads();  // (also: everybody has read the state before thread 0 rewrites it below)
+  if (tid == 0) {
+    const uint32_t i = st->nlog;
+    if (i < (uint32_t)LADDER_LOG) { st->log_m[i] = m0; st->log_kind[i] = 2u; st->log_h[i] = st->h; st->nlog = i + 1u; }
+    st->m = 0;
+    st->maxgroup = 0;
+  }
   while (m > 0) {
     if (++iters > 64u) {  // cannot happen (h doubles past N); watchdog instead of a hang
-      if (tid == 0) atomicExch(errflag, 3u);
+      if (tid == 0) atomicExch(&ctrl[CTR_ERR], 3u);
       break;
     }
     uint32_t P = 2;  // sort width: next power of two >= m
@@ -1732,9 +1870,14 @@ __global__ void __launch_bounds__(1024) k_small_rounds(const uint32_t* __restric
 __global__ void __launch_bounds__(256) k_finish(const uint32_t* __restrict__ rank, const uint8_t* __restrict__ text,
                                                 uint32_t N, uint8_t* __restrict__ out, int block_mode,
                                                 uint32_t* __restrict__ LF, uint32_t nLF,
-                                                const uint32_t* __restrict__ lastch) {
+                                                const uint32_t* __restrict__ lastch, LadderState* st,
+                                                const uint32_t* __restrict__ ctrl) {
   const uint32_t pidx = rank[0] & RANK_MASK;
   const uint32_t tid = threadIdx.x;
+  const uint32_t err = ctrl[CTR_ERR];
+  if (tid == 0) st->err = err;
+  if (err || st->m != 0u) return;  // failed (rank[] is not trustworthy), or refinement not finished yet: the host
+                                   // continues and launches k_finish again
   if (tid < nLF) {
     const uint32_t x = N / nLF;
     LF[tid] = (tid == 0) ? pidx : (rank[N - tid * x] & RANK_MASK);
@@ -1754,8 +1897,12 @@ __global__ void __launch_bounds__(256) k_finish(const uint32_t* __restrict__ ran
 __global__ void __launch_bounds__(256) k_finish_batch(const uint32_t* __restrict__ rank, uint32_t Ntot, uint32_t stride,
                                                       uint32_t nblocks, uint8_t* __restrict__ out,
                                                       uint32_t* __restrict__ LF, uint32_t nLF, uint32_t nLF_last,
-                                                      const uint32_t* __restrict__ lastch) {
+                                                      const uint32_t* __restrict__ lastch, LadderState* st,
+                                                      const uint32_t* __restrict__ ctrl) {
   const uint32_t k = blockIdx.x, tid = threadIdx.x;
+  const uint32_t err = ctrl[CTR_ERR];
+  if (k == 0 && tid == 0) st->err = err;
+  if (err || st->m != 0u) return;
   const uint32_t start = k * stride;
   const uint32_t Nk = (k + 1u == nblocks) ? Ntot - start : stride;
   const uint32_t nl = (k + 1u == nblocks) ? nLF_last : nLF;

@@ -39,6 +39,10 @@ extern "C" {
  * counters of the radix-sort look-back words.  (The reference allows < 2^31-2, Compressor.cpp:78-79.) */
 #define BWTC_CUDA_MAX_BLOCK ((uint32_t)0x3FFFFFF0u)
 
+/* Device scratch per suffix (input, text, output, rank, two key + two id buffers, staged ranks, payload bytes, status
+ * words) — an upper bound for blocks of 1 MiB and more; bwtc_cuda_scratch_bytes(n) is the exact figure a context for n-byte blocks allocates. */
+#define BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX 40
+
 typedef struct bwtc_cuda_ctx bwtc_cuda_ctx;           /* one stream + device scratch for one in-flight block */
 typedef struct bwtc_cuda_pipeline bwtc_cuda_pipeline; /* several contexts + host workers on one GPU */
 
@@ -67,6 +71,8 @@ typedef struct bwtc_cuda_stats {
   uint32_t flags;            /* bit 0: look-back kernels ran with ticket counters (watchdog fallback or BWTC_STATIC_TILES=0);
                               * bit 1: the blocks of a batch were sorted as one text; bit 2: predecessor codes packed above the ids;
                               * bit 3: ... carried as a one-byte payload array */
+  uint32_t batch_blocks;     /* blocks this record describes: 1, or the size of the batch that was sorted as one text (every
+                              * block of the batch then carries the SAME record — count it once) */
 } bwtc_cuda_stats;
 
 /* ---- library / device ------------------------------------------------------------------------ */
@@ -77,9 +83,10 @@ uint32_t    bwtc_cuda_stats_sizeof(void);           /* sizeof(bwtc_cuda_stats) t
 const char* bwtc_cuda_global_error(void);
 
 /* ---- context ------------------------------------------------------------------------------------ */
-/* Allocates a stream, device scratch (~31 bytes per suffix) and pinned staging for blocks up to
- * max_block_bytes on `device`.  Replaces the per-call malloc of divbwtf (divsufsort.c:491-493). */
+/* Allocates streams, device scratch (BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX bytes per suffix) and small pinned buffers for
+ * blocks up to max_block_bytes on `device`.  Replaces the per-call malloc of divbwtf (divsufsort.c:491-493). */
 int         bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_bytes);
+uint64_t    bwtc_cuda_scratch_bytes(uint32_t max_block_bytes);  /* device bytes such a context allocates */
 void        bwtc_cuda_ctx_destroy(bwtc_cuda_ctx* ctx);
 const char* bwtc_cuda_last_error(const bwtc_cuda_ctx* ctx);
 int         bwtc_cuda_get_stats(const bwtc_cuda_ctx* ctx, bwtc_cuda_stats* out);
@@ -147,6 +154,16 @@ int  bwtc_cuda_pipeline_set_timing(bwtc_cuda_pipeline* p, int detail);
 int  bwtc_cuda_pipeline_run(bwtc_cuda_pipeline* p, const uint8_t* const* in, uint8_t* const* out,
                             const uint32_t* sizes, uint32_t nblocks, uint32_t starts, int on_device,
                             uint32_t* LFpowers, uint32_t* nLF, uint32_t* freqs, bwtc_cuda_stats* stats);
+/* Streaming form of the same pipeline (the look-ahead driver of a compressor: read block, submit, keep reading; entropy-code
+ * block i as soon as bwtc_cuda_pipeline_wait(i) returns).  submit queues ONE block (block contract, in/out as above; LFpowers:
+ * 256 words, *nLF and freqs[256] written/incremented when the block completes; stats may be NULL) and returns at once with a
+ * ticket; the pointers must stay valid until the block has been waited for.  Queued small blocks of equal size are still
+ * batched into one device-side sort.  wait blocks (sleeping, not spinning) until that block is done and returns 0 or its
+ * negative error (message: bwtc_cuda_pipeline_error).  Each ticket must be waited for exactly once. */
+int  bwtc_cuda_pipeline_submit(bwtc_cuda_pipeline* p, const uint8_t* in, uint8_t* out, uint32_t n, uint32_t starts,
+                               int on_device, uint32_t* LFpowers, uint32_t* nLF, uint32_t* freqs,
+                               bwtc_cuda_stats* stats, uint64_t* ticket);
+int  bwtc_cuda_pipeline_wait(bwtc_cuda_pipeline* p, uint64_t ticket);
 /* Device-side timing of whatever the pipeline's streams execute between the two calls: begin records
  * an event every context stream waits on; end joins all context streams and returns elapsed ms
  * (CUDA events, all streams of this pipeline), or a negative error. */

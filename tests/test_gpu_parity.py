@@ -1,7 +1,7 @@
 """GPU parity tests (the first gate): the CUDA path, called through the C-ABI, must be bit-exact with the oracle
-on the same seeded inputs, with the golden fixtures generated from the reference, and — at BASELINE.json's
-block sizes — satisfy size-independent properties (histogram preservation, reference-inverse round trip,
-pipeline == single-context)."""
+on the same seeded inputs and with the golden fixtures generated from the reference.  BASELINE.json's block sizes
+are compared bit for bit with the compiled reference in tests/test_gpu_fullsize.py; the engine's maximum block size
+(no CPU checker finishes in test time) is covered by size-independent properties here."""
 import numpy as np
 import pytest
 
@@ -280,53 +280,6 @@ def test_every_engine_path_is_bit_exact(oracle, monkeypatch, knobs):
             assert not (flags & 1), "unexpected watchdog fallback"
     finally:
         ctx.close()
-
-
-@pytest.mark.parametrize("kind,mib", [("markov", 32), ("dna", 64), ("repetitive", 16), ("random", 64)])
-def test_full_size_properties(reference, kind, mib):
-    """BASELINE.json block sizes: size-independent properties instead of the (slow) oracle —
-    byte histogram preserved, freqs == histogram, LFpowers in range and distinct, and the REFERENCE's own
-    inverse transform (MtlSaInverseBWT via InverseBWTransform::doTransform(BWTBlock&)) restores the block."""
-    n = mib << 20
-    x = bw.generate(kind, n, seed=31)
-    ctx = bw.CudaContext(n)
-    blk = x.copy()
-    LF = np.zeros(8, np.uint32)
-    fr = np.zeros(256, np.uint32)
-    pidx = ctx.bwt_block(blk, LF, fr)
-    st = ctx.stats()
-    ctx.close()
-    assert st["n_suffixes"] == n + 1 and st["live"][0] == n + 1
-    hist = np.bincount(x, minlength=256)
-    assert (np.bincount(blk, minlength=256) == hist).all()
-    assert (fr == hist).all()
-    assert pidx == LF[0] and (LF <= n).all() and len(set(LF.tolist())) == LF.size
-    back = reference.inverse_block(blk, LF)
-    assert (back == x).all()
-
-
-def test_256mib_random_block_properties():
-    """config 4: 256 MiB block (29-bit ranks, 8 doubling-key passes, ~8.3 GB of scratch)."""
-    n = 256 << 20
-    x = bw.generate("random", n, seed=32)
-    ctx = bw.CudaContext(n)
-    blk = x.copy()
-    LF = np.zeros(8, np.uint32)
-    fr = np.zeros(256, np.uint32)
-    ctx.bwt_block(blk, LF, fr)
-    ctx.close()
-    hist = np.bincount(x, minlength=256)
-    assert (fr == hist).all() and (np.bincount(blk, minlength=256) == hist).all()
-    # spot-check ranks: LFpowers[j] is the rank of suffix N - j*x of T' = reverse(X)+0; compare the order of the
-    # 8 sampled suffixes with a direct comparison of their first 64 bytes (random bytes differ long before that)
-    N = n + 1
-    T = np.concatenate([x[::-1], np.zeros(1, np.uint8)])
-    xs = N // 8
-    pos = [0] + [N - j * xs for j in range(1, 8)]
-    keys = [bytes(T[p: p + 64]) for p in pos]
-    order_by_rank = np.argsort(LF)
-    order_by_text = sorted(range(8), key=lambda i: keys[i])
-    assert list(order_by_rank) == order_by_text
 
 
 def test_maximum_block_size_properties():
