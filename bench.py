@@ -236,8 +236,12 @@ def run_compress_leg(local_rank, world, rank):
     nblocks = 32 if world == 1 else 16
     cmd = [sys.executable, os.path.abspath(__file__), "--leg", "compress", "--leg-device", str(local_rank), "--leg-blocks",
            str(nblocks), "--leg-threads", str(threads), "--leg-seed", str(5000 + 1000 * rank)]
+    env = dict(os.environ)
+    # glibc: back malloc's mmap'ed chunks with transparent huge pages (the reference allocates and frees ~5 block sizes of
+    # scratch per block — PrecompressorBlock.cpp:41, HuffmanCoders.cpp:125-126 — one page fault per 4 KiB otherwise)
+    env.setdefault("GLIBC_TUNABLES", "glibc.malloc.hugetlb=1")
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
         out = json.loads(r.stdout.strip().splitlines()[-1])
     except Exception as e:  # noqa: BLE001
         return {"error": "compress leg failed: %s" % e}
@@ -423,6 +427,8 @@ def main_gpu(args):
                     "encoder_busy_core_s": float(vals[3]),
                     "coder_mb_per_core_s": float(vals[1]) / 1e6 / max(float(vals[3]), 1e-9),
                     "gpu_pipeline_depth": mine_c["pipeline_depth"], "leg_wall_s": tc,
+                    "reader_busy_s_rank0": mine_c.get("reader_busy_s"), "writer_busy_s_rank0": mine_c.get("writer_busy_s"),
+                    "first_pass_seconds_rank0": mine_c.get("first_pass_seconds"),
                     "note": "bound by the CPU entropy coder (MB per core-second above x cores); the GPU BWT stage runs "
                             "ahead of it (see `value` / `e2e`)"}
 

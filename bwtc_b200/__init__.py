@@ -103,6 +103,9 @@ C_ABI = [
     ("bwtc_cuda_divbwt", ctypes.c_int64, [_vp, _vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32]),
     ("bwtc_cuda_bwt_block", ctypes.c_int64, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _vp]),
     ("bwtc_cuda_bwt_block_device", ctypes.c_int64, [_vp, _vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _vp]),
+    ("bwtc_cuda_inverse_block", ctypes.c_int64, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32]),
+    ("bwtc_cuda_inverse_block_device", ctypes.c_int64, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32]),
+    ("bwtc_cuda_inverse_raw", ctypes.c_int64, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32]),
     ("bwtc_cuda_bwt_blocks", ctypes.c_int,
      [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _vp, _vp, _vp]),
     ("bwtc_cuda_num_starting_points", ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32]),
@@ -213,6 +216,20 @@ class CudaContext:
         assert block.dtype == np.uint8 and LFpowers.dtype == np.uint32
         return self._check(self._lib.bwtc_cuda_bwt_block(self._h, block.ctypes.data, block.size,
                                                           LFpowers.ctypes.data, LFpowers.size, _ptr(freqs)))
+
+    # inverse, block level: InverseBWTransform::doTransform(BWTBlock&) — InverseBWT.cpp:47-51
+    def inverse_block(self, block: np.ndarray, LFpowers: np.ndarray) -> int:
+        assert block.dtype == np.uint8 and LFpowers.dtype == np.uint32
+        return self._check(self._lib.bwtc_cuda_inverse_block(self._h, block.ctypes.data, block.size, LFpowers.ctypes.data,
+                                                              LFpowers.size))
+
+    def inverse_block_device(self, d_in: int, d_out: int, n: int, eob: int) -> int:
+        return self._check(self._lib.bwtc_cuda_inverse_block_device(self._h, d_in, d_out, n, eob))
+
+    # inverse, raw virtual: doTransform(byte* bwt, uint32 N, LFpow) — InverseBWT.hpp:49-50
+    def inverse_raw(self, bwt: np.ndarray, LFpowers: np.ndarray) -> int:
+        assert bwt.dtype == np.uint8 and LFpowers.dtype == np.uint32
+        return self._check(self._lib.bwtc_cuda_inverse_raw(self._h, bwt.ctypes.data, bwt.size, LFpowers.ctypes.data, LFpowers.size))
 
     def bwt_blocks(self, blocks, starts: int, want_freqs: bool = True):
         """bwtc_cuda_bwt_blocks: transform the given uint8 arrays IN PLACE (equal-sized runs are batched into one

@@ -4,6 +4,7 @@
 // code and bwtc_cuda_last_error() says why.
 #include "../../include/bwtc_cuda.h"
 #include "bwt_kernels.cuh"
+#include "ibwt_kernels.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -886,8 +887,10 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
         lists_pending = false;
       }
       const int K = dbg ? 1 : (first_chunk ? ctx->ladder_first : ctx->ladder_more);
-      const uint32_t seg_grid = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(m_bound, SEG_T), (uint32_t)ctx->sm_count * 16u));
       for (int k = 0; k < K && ctx->use_seg; ++k) {
+        // persistent grid; the first round behind a sort is the big one, later (often skipped) ones get a leaner grid
+        const uint32_t per_sm = (k == 0) ? 12u : 4u;
+        const uint32_t seg_grid = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(m_bound, SEG_T), (uint32_t)ctx->sm_count * per_sm));
         k_seg_round<<<seg_grid, 256, 0, st>>>(ctx->d_state, pool, ctx->d_rank, N, ep, ctx->d_ctrl());
         k_apply_ranks<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_state, pool, ctx->d_ctrl(), ctx->d_rank);
         k_commit_seg<<<1, 1, 0, st>>>(ctx->d_state, ctx->d_ctrl());
@@ -1122,6 +1125,101 @@ int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, 
     rc = phase_sort(ctx, J);
   }
   return rc;
+}
+
+// ---- inverse transform (kernels in ibwt_kernels.cuh).  block_mode: the n bytes a forward
+// bwtc_cuda_bwt_block produced (hole at eob filled with L[N-1]), result n bytes of the original block — the contract of
+// InverseBWTransform::doTransform(BWTBlock&) (InverseBWT.cpp:47-51).  raw: N = n_in bytes L[0..N) with L[eob] ignored,
+// result N-1 bytes — the virtual doTransform(byte*, uint32, LFpow) (InverseBWT.hpp:49-50).
+int64_t run_inverse(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, uint8_t* h_out, const uint8_t* in_dev, uint8_t* out_dev,
+                    uint32_t n_in, uint32_t eob) {
+  ctx->err[0] = 0;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) {
+    set_err(ctx->err, "cudaSetDevice(%d) failed", ctx->device);
+    return BWTC_CUDA_ECUDA;
+  }
+  const uint32_t N = block_mode ? n_in + 1u : n_in, n = N - 1u;
+  if (n_in == 0 || n > ctx->cap || N < 2) {
+    set_err(ctx->err, "inverse: block of %u bytes exceeds context capacity %u (or is empty)", n, ctx->cap);
+    return n > ctx->cap ? BWTC_CUDA_ETOOBIG : BWTC_CUDA_EARG;
+  }
+  if (eob >= N) {
+    set_err(ctx->err, "inverse: end-of-block position %u outside [0, %u)", eob, N);
+    return BWTC_CUDA_EARG;
+  }
+  cudaStream_t st = ctx->stream;
+  bwtc_cuda_stats& S = ctx->stats;
+  memset(&S, 0, sizeof(S));
+  S.n_suffixes = N;
+  S.batch_blocks = 1;
+  PassTimer pt{ctx};
+  const uint8_t* d_src = in_dev;
+  if (!in_dev) {
+    if (upload(ctx, ctx->d_in, h_in, n_in)) return BWTC_CUDA_ECUDA;
+    d_src = ctx->d_in;
+  }
+  uint8_t* d_dst = out_dev ? out_dev : ctx->d_out;
+  CK(ctx, cudaEventRecord(ctx->ev_begin, st));
+  CK(ctx, cudaMemsetAsync(ctx->d_zero, 0, (size_t)CTR_STICKY * 4, st));
+  if (zero_round_state(ctx, N, N, RS_TILE32, 3u)) return BWTC_CUDA_ECUDA;
+  uint32_t* keys0 = static_cast<uint32_t*>(ctx->d_keys[0]);
+  uint32_t* C = ctx->d_bhist;  // 258 words
+  k_inv_keys<<<ctx->sm_count * 8, 256, 0, st>>>(d_src, N, eob, block_mode ? 1 : 0, keys0, ctx->d_hist());
+  k_inv_ctable<<<1, 32, 0, st>>>(ctx->d_hist(), N, C);
+  CK(ctx, cudaGetLastError());
+  S.kernel_launches += 2;
+  S.algorithmic_bytes += (uint64_t)N * 5;
+  int cur = 0;
+  uint32_t pdone = 0;
+  const int rc = run_sort<uint32_t, RS_IPT32>(ctx, N, 3u, true, N - 1, &cur, &pt, &pdone);
+  if (rc) return rc;
+  const uint32_t* vals = ctx->d_idx[cur];
+  const uint32_t Sn = div_up(N, INV_K);
+  uint32_t* nxtA = ctx->d_scat;
+  uint32_t* distA = nxtA + Sn;
+  uint32_t* nxtB = distA + Sn;
+  uint32_t* distB = nxtB + Sn;
+  uint32_t* len = distB + Sn;  // 5 * ceil(N / 128) <= N words for N >= 8; tiny blocks: d_scat has N + 16 words
+  if ((uint64_t)5 * Sn > (uint64_t)N + 16) {  // N < ~8: use the (idle) second id buffer as well
+    nxtA = ctx->d_idx[cur ^ 1]; distA = nxtA + Sn; nxtB = ctx->d_scat; distB = nxtB + Sn; len = static_cast<uint32_t*>(ctx->d_keys[1]);
+  }
+  const uint32_t sgrid = div_up(Sn, 256);
+  k_inv_walk1<<<sgrid, 256, 0, st>>>(vals, N, Sn, nxtA, len, ctx->d_ctrl());
+  CK(ctx, cudaMemcpyAsync(distA, len, (size_t)Sn * 4, cudaMemcpyDeviceToDevice, st));
+  uint32_t* nin = nxtA; uint32_t* din = distA; uint32_t* nout = nxtB; uint32_t* dout = distB;
+  uint32_t rounds = 0;
+  for (uint64_t span = 1; span < (uint64_t)Sn; span <<= 1) {
+    k_inv_jump<<<sgrid, 256, 0, st>>>(nin, din, Sn, nout, dout);
+    std::swap(nin, nout);
+    std::swap(din, dout);
+    ++rounds;
+  }
+  k_inv_walk2<<<sgrid, 256, 0, st>>>(vals, len, din, C, N, Sn, d_dst, ctx->d_ctrl());
+  CK(ctx, cudaGetLastError());
+  S.kernel_launches += 2 + rounds;
+  S.algorithmic_bytes += (uint64_t)N * (4 + 4 + 1) + (uint64_t)Sn * 16 * (rounds + 1);
+  CK(ctx, cudaEventRecord(ctx->ev_end, st));
+  CK(ctx, cudaMemcpyAsync(ctx->h_ctrl(), ctx->d_ctrl(), CTR_STICKY * 4, cudaMemcpyDeviceToHost, st));
+  if (!out_dev && is_pinned_host(h_out)) CK(ctx, cudaMemcpyAsync(h_out, ctx->d_out, n, cudaMemcpyDeviceToHost, st));
+  if (host_wait(ctx, st)) return BWTC_CUDA_ECUDA;
+  if (ctx->h_ctrl()[CTR_ERR]) {
+    // the only look-back kernels here are the two digit passes; repeat with tickets (cannot happen twice)
+    if (ctx->static_tiles) {
+      ctx->static_tiles = 0;
+      return run_inverse(ctx, block_mode, h_in, h_out, in_dev ? in_dev : nullptr, out_dev, n_in, eob);
+    }
+    set_err(ctx->err, "inverse: look-back watchdog fired");
+    return BWTC_CUDA_EINTERNAL;
+  }
+  if (!out_dev && !is_pinned_host(h_out) && download_staged(ctx, h_out, ctx->d_out, n)) return BWTC_CUDA_ECUDA;
+  float ms = 0;
+  CK(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+  S.gpu_ms = ms;
+  S.rounds = rounds;
+  S.passes[0] = pdone;
+  S.live[0] = N;
+  S.flags = ctx->static_tiles ? 0u : 1u;
+  return (int64_t)n;
 }
 
 // count blocks (block contract) through one context: as ONE batch when they qualify — 2..MAX_BATCH blocks, all of
@@ -1454,6 +1552,24 @@ int64_t bwtc_cuda_bwt_block_device(bwtc_cuda_ctx* ctx, const void* d_in, void* d
   if (!d_in || !d_out || n == 0) { set_err(ctx->err, "null or empty block"); return BWTC_CUDA_EARG; }
   return run_transform(ctx, true, nullptr, nullptr, static_cast<const uint8_t*>(d_in), static_cast<uint8_t*>(d_out), n,
                        LFpowers, nLFpowers, freqs);
+}
+
+int64_t bwtc_cuda_inverse_block(bwtc_cuda_ctx* ctx, uint8_t* block, uint32_t n, const uint32_t* LFpowers, uint32_t nLFpowers) {
+  if (!ctx) { set_err(g_err, "null context"); return BWTC_CUDA_EARG; }
+  if (!block || n == 0 || !LFpowers || nLFpowers < 1) { set_err(ctx->err, "null or empty block / no starting point"); return BWTC_CUDA_EARG; }
+  return run_inverse(ctx, true, block, block, nullptr, nullptr, n, LFpowers[0]);
+}
+
+int64_t bwtc_cuda_inverse_block_device(bwtc_cuda_ctx* ctx, const void* d_in, void* d_out, uint32_t n, uint32_t eob) {
+  if (!ctx) { set_err(g_err, "null context"); return BWTC_CUDA_EARG; }
+  if (!d_in || !d_out || n == 0) { set_err(ctx->err, "null or empty block"); return BWTC_CUDA_EARG; }
+  return run_inverse(ctx, true, nullptr, nullptr, static_cast<const uint8_t*>(d_in), static_cast<uint8_t*>(d_out), n, eob);
+}
+
+int64_t bwtc_cuda_inverse_raw(bwtc_cuda_ctx* ctx, uint8_t* bwt, uint32_t N, const uint32_t* LFpowers, uint32_t nLFpowers) {
+  if (!ctx) { set_err(g_err, "null context"); return BWTC_CUDA_EARG; }
+  if (!bwt || N < 2 || !LFpowers || nLFpowers < 1) { set_err(ctx->err, "null / too short input or no starting point"); return BWTC_CUDA_EARG; }
+  return run_inverse(ctx, false, bwt, bwt, nullptr, nullptr, N, LFpowers[0]);
 }
 
 uint32_t bwtc_cuda_num_starting_points(uint32_t block_bytes, uint32_t starts) {

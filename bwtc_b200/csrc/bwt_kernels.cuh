@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(256) k_build_keys(const uint32_t* __restrict__
   __shared__ uint32_t s_wtot[WARPS];
   __shared__ uint32_t s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (ld_relaxed_u32(ctrl + CTR_ERR)) return;
+  if (ctrl[CTR_ERR]) return;
 #pragma unroll
   for (int p = 0; p < 8; ++p) s_hist[p * 256 + tid] = 0;
   __syncthreads();
@@ -939,7 +939,8 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
     __syncthreads();
     tile = s_tile;
   }
-  if (ld_relaxed_u32(ctrl + CTR_ERR)) return;  // sticky: an earlier kernel of this block failed (see k_radix_pass)
+  const uint32_t err_at_entry = ctrl[CTR_ERR];  // sticky: an earlier kernel of this block failed (see k_radix_pass);
+                                                // a plain load, tested behind the record loads it is issued with
   const uint32_t m = rp.m;
   const uint32_t tile_base = tile * (uint32_t)TILE;
   if (tile_base >= m) return;
@@ -978,6 +979,7 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
       id[k] = (j < m) ? idx[j] : 0u;
     }
   }
+  if (err_at_entry) return;
   uint32_t pc0 = 0, pc1 = 0;  // packed predecessor codes of the 8 records (one byte each)
   if (ROUND0 && rp.packed == 2u) {
     if (tile_base + TILE <= m) {
@@ -1258,7 +1260,7 @@ __global__ void __launch_bounds__(256) k_scatter_bucket(const uint32_t* __restri
                                                         const uint32_t* __restrict__ tile_woff, uint32_t ntiles,
                                                         uint32_t nbuckets, uint32_t b, uint32_t tile_records,
                                                         uint32_t* __restrict__ rank, const uint32_t* __restrict__ ctrl) {
-  if (ld_relaxed_u32(ctrl + CTR_ERR)) return;  // sticky error: the staged pairs may be incomplete
+  if (ctrl[CTR_ERR]) return;  // sticky error: the staged pairs may be incomplete
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t nw = gridDim.x * (blockDim.x >> 5);
   for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < ntiles; tile += nw) {
@@ -1396,10 +1398,10 @@ __global__ void __launch_bounds__(256) k_gather_chunks(const uint32_t* __restric
                                                        uint32_t* __restrict__ out_id,
                                                        const LadderState* __restrict__ st, const uint32_t* __restrict__ ctrl) {
   // st != nullptr: speculative launch — only if the next step consumes the lists (k_commit_sort decided)
-  if (st && !st->lists) return;
-  if (ld_relaxed_u32(ctrl + CTR_ERR)) return;
   const uint32_t tile = blockIdx.x;
+  const uint32_t wanted = st ? st->lists : 1u, err = ctrl[CTR_ERR];  // (all four loads are issued before the first branch)
   const uint32_t c = cnt[tile], dst = excl[tile];
+  if (!wanted || err) return;
   const size_t src = (size_t)tile * tile_records;
   for (uint32_t t = threadIdx.x; t < c; t += blockDim.x) {
     out_nr[dst + t] = stage_nr[src + t];
@@ -1419,7 +1421,7 @@ __global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restr
                                                          int npass, const uint32_t* __restrict__ ctrl) {
   __shared__ uint32_t s_hist[8 * 256];
   const int tid = threadIdx.x;
-  if (ld_relaxed_u32(ctrl + CTR_ERR)) return;
+  if (ctrl[CTR_ERR]) return;
 #pragma unroll
   for (int p = 0; p < 8; ++p) s_hist[p * 256 + tid] = 0;
   __syncthreads();
@@ -1465,8 +1467,8 @@ __global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const LadderSt
   __shared__ uint32_t s_wa[8], s_wb[8];
   __shared__ uint32_t s_start, s_end, s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (!ladder_wants_seg(*st) || ld_relaxed_u32(ctrl + CTR_ERR)) return;
-  const uint32_t m_in = st->m, h = st->h;
+  const uint32_t m_in = st->m, h = st->h, st_maxgroup = st->maxgroup, st_lists = st->lists, err = ctrl[CTR_ERR];
+  if (!(st_lists && m_in > (uint32_t)SMALL_MAX && st_maxgroup <= (uint32_t)SEG_MAXGROUP) || err) return;  // ladder_wants_seg
   // the six list pointers live in shared memory (they would cost 12 registers across the tile loop)
   __shared__ uint32_t* s_ptr[6];  // [0] nr_in [1] id_in [2] nr_out [3] id_out [4] upd_id [5] upd_nr
   if (tid == 0) {
@@ -1709,7 +1711,8 @@ __global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const LadderSt
 // became final.  The count is read from ctrl[CTR_UPD] on the device (no host round trip in between).
 __global__ void __launch_bounds__(256) k_apply_ranks(const LadderState* __restrict__ st, PoolPtrs pool,
                                                      const uint32_t* __restrict__ ctrl, uint32_t* __restrict__ rank) {
-  if (!ladder_wants_seg(*st) || ld_relaxed_u32(ctrl + CTR_ERR)) return;  // the round did not run
+  const uint32_t st_m = st->m, st_maxgroup = st->maxgroup, st_lists = st->lists, err = ctrl[CTR_ERR];
+  if (!(st_lists && st_m > (uint32_t)SMALL_MAX && st_maxgroup <= (uint32_t)SEG_MAXGROUP) || err) return;  // the round did not run
   int fslot[4];
   ladder_free_slots(st->sel, fslot);
   const uint32_t* __restrict__ upd_id = pool.p[fslot[2]];
@@ -1739,7 +1742,7 @@ __global__ void __launch_bounds__(1024) k_small_rounds(LadderState* st, PoolPtrs
   __shared__ uint32_t s_m;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t m0 = st->m;
-  if (!st->lists || m0 == 0u || m0 > (uint32_t)SMALL_MAX || ld_relaxed_u32(ctrl + CTR_ERR)) return;  // not (yet) the tail
+  if (!st->lists || m0 == 0u || m0 > (uint32_t)SMALL_MAX || ctrl[CTR_ERR]) return;  // not (yet) the tail
   const uint32_t* __restrict__ list = pool.p[st->sel >> 4];
   for (int j = tid; j < SMALL_MAX; j += 1024) s_id[j] = (j < (int)m0) ? list[j] : 0u;
   uint32_t m = m0;

@@ -33,9 +33,10 @@ struct Lookahead {
   std::vector<bwtc_cuda_pipeline*> pipes;
   std::vector<int> devices;
   uint32 maxBlock;
+  int depth;
   size_t next;
   std::map<const byte*, Pending*> table;
-  Lookahead() : maxBlock(0), next(0) {}
+  Lookahead() : maxBlock(0), depth(0), next(0) {}
 };
 Lookahead& la() {
   static Lookahead L;
@@ -158,6 +159,40 @@ uint64 CudaBWTransform::suggestedBlockSize(uint64 memory_budget) const {
   return b > (32u << 20) ? (32u << 20) : b;
 }
 
+/* ---- inverse ------------------------------------------------------------------------------------------------- */
+CudaInverseBWTransform::CudaInverseBWTransform(int device) : m_device(device < 0 ? default_device() : device), m_ctx(0), m_cap(0) {}
+
+CudaInverseBWTransform::~CudaInverseBWTransform() {
+  if (m_ctx) bwtc_cuda_ctx_destroy(m_ctx);
+}
+
+uint64 CudaInverseBWTransform::maxBlockSize(uint64 memory_budget) const {
+  if (memory_budget <= (3u << 20) + 64) return 0;
+  uint64 b = (memory_budget - (3u << 20)) / BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX - 1;
+  return b > BWTC_CUDA_MAX_BLOCK ? BWTC_CUDA_MAX_BLOCK : b;
+}
+
+void CudaInverseBWTransform::doTransform(byte *bwt, uint32 n, const std::vector<uint32>& LFpow) {
+  if (n < 2 || LFpow.empty()) return;  /* one row = the end-of-block symbol alone: an empty block */
+  if (!m_ctx || n - 1 > m_cap) {
+    uint64 want = n - 1 < (1u << 20) ? (1u << 20) : n - 1;
+    if (m_ctx) {
+      if ((uint64)m_cap * 2 > want) want = (uint64)m_cap * 2;
+      bwtc_cuda_ctx_destroy(m_ctx);
+      m_ctx = 0;
+    }
+    if (want > BWTC_CUDA_MAX_BLOCK) want = BWTC_CUDA_MAX_BLOCK;
+    const int rc = bwtc_cuda_ctx_create(&m_ctx, m_device, (uint32)want);
+    if (rc != 0) {
+      m_ctx = 0;
+      throw std::runtime_error(std::string("bwtc::CudaInverseBWTransform: cannot create CUDA context: ") + bwtc_cuda_global_error());
+    }
+    m_cap = (uint32)want;
+  }
+  const long long rc = bwtc_cuda_inverse_raw(m_ctx, bwt, n, &LFpow[0], (uint32)LFpow.size());
+  if (rc < 0) throw std::runtime_error(std::string("bwtc::CudaInverseBWTransform::doTransform failed: ") + bwtc_cuda_last_error(m_ctx));
+}
+
 /* ---- look-ahead ---------------------------------------------------------------------------------------------- */
 void CudaBWTransform::shutdownLookahead() {
   Lookahead& L = la();
@@ -175,11 +210,19 @@ void CudaBWTransform::shutdownLookahead() {
 }
 
 void CudaBWTransform::configureLookahead(const std::vector<int>& devices, int depth, uint32 maxBlockBytes) {
+  std::vector<int> devs = devices;
+  if (devs.empty()) devs.push_back(default_device());
+  {
+    /* an idle configuration that already fits is kept: creating the per-GPU pipelines (device scratch for `depth`
+     * blocks in flight, pinned staging) costs a few hundred milliseconds, a compressor object does not own them */
+    Lookahead& L = la();
+    std::lock_guard<std::mutex> g(L.mu);
+    if (!L.pipes.empty() && L.devices == devs && L.depth == depth && L.maxBlock >= maxBlockBytes && L.table.empty()) return;
+  }
   shutdownLookahead();
   Lookahead& L = la();
   std::lock_guard<std::mutex> g(L.mu);
-  std::vector<int> devs = devices;
-  if (devs.empty()) devs.push_back(default_device());
+  L.depth = depth;
   for (size_t i = 0; i < devs.size(); ++i) {
     bwtc_cuda_pipeline* p = 0;
     const int rc = bwtc_cuda_pipeline_create(&p, devs[i], depth < 1 ? 1 : depth, maxBlockBytes);

@@ -74,4 +74,27 @@ class CudaBWTransform : public BWTransform {
 
 } // namespace bwtc
 
+#include "InverseBWT.hpp"
+
+namespace bwtc {
+
+/* Inverse transform on the GPU behind the reference's InverseBWTransform interface (bwtransforms/InverseBWT.hpp:45-55),
+ * next to MtlSaInverseBWTransform (MtlSaInverseBWT.hpp:42-51).  The patched giveInverseTransformer() (InverseBWT.cpp:42-45
+ * takes no argument) returns it when the environment variable BWTC_CUDA_INVERSE is set to a non-zero value.
+ * The raw virtual is overridden; the non-virtual block wrapper doTransform(BWTBlock&) (InverseBWT.cpp:47-51) works unchanged
+ * on top of it.  Only LFpowers[0] is used: the device makes its own, far denser starting points. */
+class CudaInverseBWTransform : public InverseBWTransform {
+ public:
+  explicit CudaInverseBWTransform(int device = -1);
+  virtual ~CudaInverseBWTransform();
+  virtual uint64 maxBlockSize(uint64 memory_budget) const;
+  virtual void doTransform(byte *bwt, uint32 n, const std::vector<uint32>& LFpow);
+ private:
+  int m_device;
+  bwtc_cuda_ctx* m_ctx;
+  uint32 m_cap;
+};
+
+} // namespace bwtc
+
 #endif

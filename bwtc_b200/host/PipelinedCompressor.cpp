@@ -300,7 +300,9 @@ size_t PipelinedCompressor::compress(size_t threads) {
   for (size_t t = 0; t < encoders.size(); ++t) encoders[t].join();
   S.cvWrite.notify_all();
   writer.join();
-  if (gpu) CudaBWTransform::shutdownLookahead();
+  /* the per-GPU pipelines stay configured for the next compress() of this process (CudaBWTransform::shutdownLookahead
+   * releases them); after a failure they are torn down, which also waits for blocks still in flight */
+  if (gpu && S.failed) CudaBWTransform::shutdownLookahead();
   if (S.failed) {
     while (!S.writeQueue.empty()) { delete S.writeQueue.front(); S.writeQueue.pop_front(); }
     throw std::runtime_error("bwtc::PipelinedCompressor: " + S.error);

@@ -192,6 +192,9 @@ long long b200_uncompress_file(const char* in, const char* out) {
   return (long long)sz;
 }
 
+/* Releases the look-ahead pipelines (device scratch, worker threads) kept between compress() calls. */
+void b200_shutdown(void) { bwtc::CudaBWTransform::shutdownLookahead(); }
+
 int b200_is_valid_choice(char c) { return bwtc::BWTManager::isValidChoice(c) ? 1 : 0; }
 
 } /* extern "C" */

@@ -15,6 +15,8 @@
  *                                              hole-fill fused on the device)
  *   bwtc_cuda_num_starting_points          <-  BWTManager::setStartingPoints + BWTBlock::prepareLFpowers
  *                                              bwtransforms/BWTManager.cpp:60-64, BWTBlock.cpp:104-108
+ *   bwtc_cuda_inverse_block / _raw         <-  InverseBWTransform::doTransform(BWTBlock&) / (byte*, uint32, LFpow)
+ *                                              bwtransforms/InverseBWT.cpp:47-51, InverseBWT.hpp:49-50 (MtlSaInverseBWT.cpp)
  *   bwtc_cuda_pipeline_*                   <-  the per-slice loop of Compressor::compress
  *                                              Compressor.cpp:100-109 (independent BWT blocks), batched
  *                                              with look-ahead over several in-flight blocks per GPU
@@ -135,6 +137,15 @@ int64_t bwtc_cuda_bwt_block_device(bwtc_cuda_ctx* ctx, const void* d_in, void* d
 #define BWTC_CUDA_MAX_BATCH 64
 int bwtc_cuda_bwt_blocks(bwtc_cuda_ctx* ctx, void* const* blocks, const uint32_t* sizes, uint32_t count,
                          uint32_t starts, int on_device, uint32_t* LFpowers, uint32_t* nLFpowers, uint32_t* freqs);
+/* ---- inverse transform: InverseBWTransform::doTransform (InverseBWT.hpp:45-55) ---------------- */
+/* Block level (InverseBWT.cpp:47-51): block holds the n bytes a forward block transform produced, LFpowers its starting
+ * points (only LFpowers[0], the end-of-block position, is needed: the device makes its own, far denser samples).  The
+ * original n bytes are restored IN PLACE; the byte after the block is never touched.  Returns n. */
+int64_t bwtc_cuda_inverse_block(bwtc_cuda_ctx* ctx, uint8_t* block, uint32_t n, const uint32_t* LFpowers, uint32_t nLFpowers);
+int64_t bwtc_cuda_inverse_block_device(bwtc_cuda_ctx* ctx, const void* d_in, void* d_out, uint32_t n, uint32_t eob);
+/* Raw virtual doTransform(byte* bwt, uint32 N, LFpow) (InverseBWT.hpp:49-50): bwt[0..N) = L with bwt[LFpowers[0]] ignored;
+ * on return bwt[0..N-1) is the original block (bwt[N-1] is left as it was).  Returns N-1. */
+int64_t bwtc_cuda_inverse_raw(bwtc_cuda_ctx* ctx, uint8_t* bwt, uint32_t N, const uint32_t* LFpowers, uint32_t nLFpowers);
 /* BWTManager::setStartingPoints clamp + BWTBlock::prepareLFpowers sizing. */
 uint32_t bwtc_cuda_num_starting_points(uint32_t block_bytes, uint32_t starts);
 

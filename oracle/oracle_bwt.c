@@ -135,3 +135,46 @@ int64_t oracle_bwt_block(uint8_t* buf, uint32_t n, uint32_t starts, uint32_t* LF
   buf[n] = next;
   return pidx;
 }
+
+/* ---- inverse transform -----------------------------------------------------------------
+ * Raw virtual InverseBWTransform::doTransform(byte* bwt, uint32 N, LFpow) restated as the plain LF walk of
+ * FastInverseBWTransform (InverseBWT.cpp:58-115): count[] with the end-of-block row counted as the smallest symbol
+ * (:74-77), rank of every row among equal characters (:79-91), prefix sums (:92), then follow
+ * position -> count[ch] + rank from row 0 until the end-of-block row is reached, writing the original bytes in
+ * forward order (:100-110).  MtlSaInverseBWTransform (what giveInverseTransformer returns, InverseBWT.cpp:42-45)
+ * computes the same function with several chains; tests/test_oracle.py pins this restatement on it.
+ * bwt: N bytes L[0..N) with bwt[eob] ignored; on return bwt[0..N-1) is the original block.  Returns N-1 or < 0. */
+int64_t oracle_inverse_raw(uint8_t* bwt, uint32_t N, uint32_t eob) {
+  if (!bwt || N < 1 || eob >= N) return -1;
+  uint32_t* rank = (uint32_t*)malloc((size_t)N * 4);
+  uint8_t* L = (uint8_t*)malloc(N);
+  if (!rank || !L) { free(rank); free(L); return -2; }
+  memcpy(L, bwt, N);
+  uint64_t count[258];
+  memset(count, 0, sizeof count);
+  count[0] = 1;  /* the end-of-block symbol */
+  rank[eob] = 0;
+  for (uint32_t p = 0; p < N; ++p)
+    if (p != eob) rank[p] = (uint32_t)count[(uint32_t)L[p] + 1]++;
+  uint64_t acc = 0;
+  for (int c = 0; c < 257; ++c) { uint64_t t = count[c]; count[c] = acc; acc += t; }  /* count[c+1] = symbols < c */
+  uint32_t index = 0, position = 0;
+  while (position != eob && index < N - 1) {
+    uint8_t ch = L[position];
+    bwt[index++] = ch;
+    position = (uint32_t)(count[(uint32_t)ch + 1] + rank[position]);
+  }
+  free(rank); free(L);
+  return index == N - 1 ? (int64_t)index : -3;  /* -3: not a valid transform (the cycle closed early) */
+}
+
+/* Block level: InverseBWTransform::doTransform(BWTBlock&) (InverseBWT.cpp:47-51) re-opens the hole
+ * (*block.end() = data[LFpowers[0]]) and inverts n+1 rows.  buf: n bytes + one writable slot (preserved). */
+int64_t oracle_inverse_block(uint8_t* buf, uint32_t n, uint32_t eob) {
+  if (!buf || n == 0 || eob > n) return -1;
+  uint8_t next = buf[n];
+  buf[n] = buf[eob];
+  int64_t rc = oracle_inverse_raw(buf, n + 1, eob);
+  buf[n] = next;
+  return rc;
+}

@@ -42,6 +42,10 @@ class Oracle:
         self.lib.oracle_bwt_raw.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p,
                                             ctypes.c_uint32, ctypes.c_void_p]
         self.lib.oracle_suffix_array.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
+        self.lib.oracle_inverse_block.restype = ctypes.c_int64
+        self.lib.oracle_inverse_block.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]
+        self.lib.oracle_inverse_raw.restype = ctypes.c_int64
+        self.lib.oracle_inverse_raw.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]
         self.lib.oracle_num_starting_points.restype = ctypes.c_uint32
         self.lib.oracle_num_starting_points.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
 
@@ -62,6 +66,12 @@ class Oracle:
         rc = self.lib.oracle_bwt_raw(buf.ctypes.data, buf.ctypes.data, T.size, LF.ctypes.data, nLF,
                                      fr.ctypes.data if want_freqs else None)
         return rc, buf, LF, fr
+
+    def inverse_block(self, bwt, eob, guard=0xAB):
+        buf = np.concatenate([bwt, np.array([guard], np.uint8)])
+        rc = self.lib.oracle_inverse_block(buf.ctypes.data, bwt.size, int(eob))
+        assert buf[-1] == guard and rc == bwt.size, rc
+        return buf[:-1].copy()
 
     def suffix_array(self, T):
         SA = np.zeros(T.size, np.uint32)

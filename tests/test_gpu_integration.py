@@ -100,3 +100,18 @@ def test_sharded_gpu_parts_merge_to_the_reference_file(tmp_path):
         parts.append(p)
     run_tool("merge_parts", tmp_path / "merged.bwtc", "H", *parts)
     assert (tmp_path / "ref.bwtc").read_bytes() == (tmp_path / "merged.bwtc").read_bytes()
+
+
+@pytest.mark.parametrize("coder,mem,mib", [("H", 5667979, 6), ("H", 90687655, 40), ("B", 5667979, 2)])
+def test_reference_decompressor_with_cuda_inverse(tmp_path, coder, mem, mib, monkeypatch):
+    """SURVEY.md §8f row f4 through the reference's own interface: Decompressor::decompress (Decompressor.cpp:58-94) with
+    the patched giveInverseTransformer() returning bwtc::CudaInverseBWTransform (BWTC_CUDA_INVERSE=1) restores the input
+    byte for byte from a .bwtc written by the UNMODIFIED reference."""
+    need_libs()
+    x = mixed_input(mib << 20, seed=21)
+    src = tmp_path / "in.bin"
+    x.tofile(src)
+    run_tool("compress", "cpu", src, tmp_path / "ref.bwtc", mem, coder, 8, tool=REFTOOL)
+    monkeypatch.setenv("BWTC_CUDA_INVERSE", "1")
+    run_tool("uncompress", tmp_path / "ref.bwtc", tmp_path / "back.bin")
+    assert (tmp_path / "back.bin").read_bytes() == x.tobytes()

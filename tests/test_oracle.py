@@ -138,3 +138,15 @@ def test_forward_inverse_roundtrip(oracle, reference):
 def test_num_starting_points(oracle):
     f = oracle.lib.oracle_num_starting_points
     assert f(256, 8) == 1 and f(257, 8) == 8 and f(1000, 0) == 1 and f(1000, 300) == 256 and f(10, 256) == 1
+
+
+def test_oracle_inverse_matches_reference_inverse(oracle, reference):
+    """the oracle's inverse restatement (plain LF walk, InverseBWT.cpp:58-115) pinned on the
+    reference's own InverseBWTransform::doTransform(BWTBlock&) (MtlSaInverseBWT) and on the forward transform."""
+    rng = np.random.default_rng(99)
+    for n, sigma, starts in [(1, 2, 8), (2, 2, 8), (3, 1, 1), (300, 4, 8), (5000, 256, 256), (70001, 64, 7), (4096, 2, 1)]:
+        x = rng.integers(0, sigma, n).astype(np.uint8)
+        b, LF, fr = reference.block(x, starts)
+        back_ref = reference.inverse_block(b, LF)
+        back_orc = oracle.inverse_block(b, LF[0])
+        assert (back_ref == x).all() and (back_orc == x).all(), (n, sigma, starts)
