@@ -80,6 +80,15 @@ class Stats(ctypes.Structure):
         }
 
 
+RUNS_OVERFLOW = 0xFFFFFFFF
+
+
+class Runs(ctypes.Structure):
+    """Mirror of ``bwtc_cuda_runs`` (include/bwtc_cuda.h)."""
+
+    _fields_ = [("capacity", ctypes.c_uint32), ("count", ctypes.c_uint32), ("symbol", ctypes.c_void_p), ("start", ctypes.c_void_p)]
+
+
 _u8p = ctypes.POINTER(ctypes.c_uint8)
 _u32p = ctypes.POINTER(ctypes.c_uint32)
 _vp = ctypes.c_void_p
@@ -103,6 +112,7 @@ C_ABI = [
     ("bwtc_cuda_divbwt", ctypes.c_int64, [_vp, _vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32]),
     ("bwtc_cuda_bwt_block", ctypes.c_int64, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _vp]),
     ("bwtc_cuda_bwt_block_device", ctypes.c_int64, [_vp, _vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _vp]),
+    ("bwtc_cuda_bwt_block_runs", ctypes.c_int64, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _vp, _vp]),
     ("bwtc_cuda_inverse_block", ctypes.c_int64, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32]),
     ("bwtc_cuda_inverse_block_device", ctypes.c_int64, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32]),
     ("bwtc_cuda_inverse_raw", ctypes.c_int64, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32]),
@@ -119,6 +129,8 @@ C_ABI = [
     ("bwtc_cuda_pipeline_submit", ctypes.c_int,
      [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_uint64)]),
     ("bwtc_cuda_pipeline_wait", ctypes.c_int, [_vp, ctypes.c_uint64]),
+    ("bwtc_cuda_pipeline_submit_runs", ctypes.c_int,
+     [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_uint64)]),
     ("bwtc_cuda_pipeline_timing_begin", ctypes.c_int, [_vp]),
     ("bwtc_cuda_pipeline_timing_end", ctypes.c_float, [_vp]),
 ]
@@ -216,6 +228,18 @@ class CudaContext:
         assert block.dtype == np.uint8 and LFpowers.dtype == np.uint32
         return self._check(self._lib.bwtc_cuda_bwt_block(self._h, block.ctypes.data, block.size,
                                                           LFpowers.ctypes.data, LFpowers.size, _ptr(freqs)))
+
+    def bwt_block_runs(self, block: np.ndarray, LFpowers: np.ndarray, freqs: Optional[np.ndarray], capacity: int):
+        """bwtc_cuda_bwt_block_runs: the block transform + the maximal runs of its output (symbol[], start[]) when there
+        are at most `capacity` of them, else None."""
+        sym = np.zeros(max(capacity, 1), np.uint8)
+        start = np.zeros(max(capacity, 1), np.uint32)
+        r = Runs(capacity, 0, sym.ctypes.data, start.ctypes.data)
+        pidx = self._check(self._lib.bwtc_cuda_bwt_block_runs(self._h, block.ctypes.data, block.size, LFpowers.ctypes.data,
+                                                               LFpowers.size, _ptr(freqs), ctypes.addressof(r)))
+        if r.count == RUNS_OVERFLOW:
+            return pidx, None
+        return pidx, (sym[: r.count].copy(), start[: r.count].copy())
 
     # inverse, block level: InverseBWTransform::doTransform(BWTBlock&) — InverseBWT.cpp:47-51
     def inverse_block(self, block: np.ndarray, LFpowers: np.ndarray) -> int:

@@ -433,6 +433,7 @@ struct Job {
   uint32_t nLF = 0;
   uint32_t* freqs = nullptr;
   const BatchSpec* bs = nullptr;   // batch of blocks (block contract): the fields above come from *bs
+  bwtc_cuda_runs* runs = nullptr;  // run statistics wanted (single block, block contract)
   // ---- phase A
   uint32_t N = 0, bstride = 0, blk_bits = 0;
   bool sentinel_outside_alphabet = false;
@@ -911,6 +912,20 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
                                   ctx->d_state, ctx->d_ctrl());
     CK(ctx, cudaGetLastError());
     S.kernel_launches++;
+    if (J.runs && !bs && J.block_mode) {
+      // run statistics of the (finished) output: symbols -> d_aux[0], start positions -> d_scat, both idle by now; tile
+      // counts in the look-back status area (cleared again before any later digit pass uses it)
+      const uint32_t rtiles = div_up(n, RUN_TILE);
+      uint32_t* rcnt = ctx->d_status + (size_t)LB_PAD_ROWS * 256u;
+      uint32_t* rexcl = rcnt + rtiles;
+      const uint32_t cap_dev = std::min<uint32_t>(J.runs->capacity, n);
+      k_run_count<<<rtiles, 256, 0, st>>>(J.d_dst, n, rcnt);
+      k_scan_tile_counts<<<1, 1024, 0, st>>>(rcnt, rexcl, rtiles);
+      k_run_emit<<<rtiles, 256, 0, st>>>(J.d_dst, n, rcnt, rexcl, rtiles, cap_dev, ctx->d_aux[0], ctx->d_scat, &ctx->d_state->nruns);
+      CK(ctx, cudaGetLastError());
+      S.kernel_launches += 3;
+      S.algorithmic_bytes += 2ull * n;
+    }
     CK(ctx, cudaEventRecord(ctx->ev_end, st));
     CK(ctx, cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(LadderState), cudaMemcpyDeviceToHost, st));
     if (bs) CK(ctx, cudaMemcpyAsync(h_bLF, ctx->d_LF, (size_t)bs->nblocks * 256 * 4, cudaMemcpyDeviceToHost, st));
@@ -1069,6 +1084,17 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
       }
     }
   }
+  if (finished && J.runs && !bs && J.block_mode) {
+    const uint32_t cnt = ctx->h_state->nruns;
+    if (cnt <= J.runs->capacity && cnt <= n && J.runs->symbol && J.runs->start) {
+      if (download_staged(ctx, J.runs->symbol, ctx->d_aux[0], cnt)) return BWTC_CUDA_ECUDA;
+      if (download_staged(ctx, reinterpret_cast<uint8_t*>(J.runs->start), reinterpret_cast<const uint8_t*>(ctx->d_scat), (size_t)cnt * 4))
+        return BWTC_CUDA_ECUDA;
+      J.runs->count = cnt;
+    } else {
+      J.runs->count = BWTC_CUDA_RUNS_OVERFLOW;
+    }
+  }
   // ---- results for the caller: LFpowers, freqs (incremented only now that the block has succeeded)
   if (bs) {
     const uint32_t* h_bhist = reinterpret_cast<const uint32_t*>(ctx->h_batch + MAX_BATCH * sizeof(void*));
@@ -1105,8 +1131,10 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
 // intact on the device, so this works for in-place device buffers too; nothing was written to LFpowers / freqs.
 int64_t run_transform(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, uint8_t* h_out, const uint8_t* in_dev,
                       uint8_t* out_dev, uint32_t n, uint32_t* LF, uint32_t nLF, uint32_t* freqs,
-                      const BatchSpec* bs = nullptr) {
+                      const BatchSpec* bs = nullptr, bwtc_cuda_runs* runs = nullptr) {
   Job J;
+  J.runs = runs;
+  if (runs) runs->count = BWTC_CUDA_RUNS_OVERFLOW;
   J.block_mode = block_mode;
   J.h_in = h_in;
   J.h_out = h_out;
@@ -1238,7 +1266,8 @@ bool batchable(const bwtc_cuda_ctx* ctx, const uint32_t* sizes, uint32_t count) 
 }
 
 int transform_batch(bwtc_cuda_ctx* ctx, const void* const* in, void* const* out, const uint32_t* sizes, uint32_t count,
-                    uint32_t starts, bool on_device, uint32_t* LF, uint32_t* nLF, uint32_t* freqs, bwtc_cuda_stats* stats) {
+                    uint32_t starts, bool on_device, uint32_t* LF, uint32_t* nLF, uint32_t* freqs, bwtc_cuda_stats* stats,
+                    bwtc_cuda_runs* runs = nullptr /* count == 1, host block only */) {
   for (uint32_t k = 0; k < count; ++k) {
     if (!in[k] || !out[k] || sizes[k] == 0) { set_err(ctx->err, "null or empty block %u", k); return BWTC_CUDA_EARG; }
     nLF[k] = bwtc_cuda_num_starting_points(sizes[k], starts);
@@ -1270,7 +1299,7 @@ int transform_batch(bwtc_cuda_ctx* ctx, const void* const* in, void* const* out,
                          LF + (size_t)k * 256, nLF[k], fr);
     else
       rc = run_transform(ctx, true, static_cast<const uint8_t*>(in[k]), static_cast<uint8_t*>(out[k]), nullptr, nullptr, sizes[k],
-                         LF + (size_t)k * 256, nLF[k], fr);
+                         LF + (size_t)k * 256, nLF[k], fr, nullptr, count == 1 ? runs : nullptr);
     ctx->stats.batch_blocks = 1;
     if (stats) stats[k] = ctx->stats;
     if (rc < 0) return (int)rc;
@@ -1530,6 +1559,13 @@ int64_t bwtc_cuda_bwt_block(bwtc_cuda_ctx* ctx, uint8_t* block, uint32_t n, uint
   return run_transform(ctx, true, block, block, nullptr, nullptr, n, LFpowers, nLFpowers, freqs);
 }
 
+int64_t bwtc_cuda_bwt_block_runs(bwtc_cuda_ctx* ctx, uint8_t* block, uint32_t n, uint32_t* LFpowers, uint32_t nLFpowers,
+                                 uint32_t* freqs, bwtc_cuda_runs* runs) {
+  if (!ctx) { set_err(g_err, "null context"); return BWTC_CUDA_EARG; }
+  if (!block || n == 0) { set_err(ctx->err, "null or empty block"); return BWTC_CUDA_EARG; }
+  return run_transform(ctx, true, block, block, nullptr, nullptr, n, LFpowers, nLFpowers, freqs, nullptr, runs);
+}
+
 int bwtc_cuda_bwt_blocks(bwtc_cuda_ctx* ctx, void* const* blocks, const uint32_t* sizes, uint32_t count, uint32_t starts,
                          int on_device, uint32_t* LFpowers, uint32_t* nLFpowers, uint32_t* freqs) {
   if (!ctx) { set_err(g_err, "null context"); return BWTC_CUDA_EARG; }
@@ -1596,6 +1632,7 @@ struct PipeItem {
   uint32_t* nLF = nullptr;
   uint32_t* freqs = nullptr;
   bwtc_cuda_stats* stats = nullptr;
+  bwtc_cuda_runs* runs = nullptr;
   uint64_t ticket = 0;
   int rc = 0;
   bool done = false;
@@ -1639,12 +1676,12 @@ void pipeline_worker(bwtc_cuda_pipeline* p, bwtc_cuda_ctx* c) {
       grp.push_back(p->queue.front());
       p->queue.pop_front();
       // consecutive small blocks of equal size (same contract parameters) go to ONE device-side sort
-      if (grp[0]->n <= p->batch_max_block) {
+      if (grp[0]->n <= p->batch_max_block && !grp[0]->runs) {
         sizes.assign(1, grp[0]->n);
         const uint32_t lim = std::min<uint32_t>(MAX_BATCH, p->batch_blocks);
         while (!p->queue.empty() && grp.size() < lim) {
           const PipeItem& nx = *p->queue.front();
-          if (nx.starts != grp[0]->starts || nx.on_device != grp[0]->on_device || (nx.freqs == nullptr) != (grp[0]->freqs == nullptr)) break;
+          if (nx.starts != grp[0]->starts || nx.on_device != grp[0]->on_device || (nx.freqs == nullptr) != (grp[0]->freqs == nullptr) || nx.runs) break;
           sizes.push_back(nx.n);
           if (!batchable(c, sizes.data(), (uint32_t)sizes.size())) { sizes.pop_back(); break; }
           grp.push_back(p->queue.front());
@@ -1658,7 +1695,7 @@ void pipeline_worker(bwtc_cuda_pipeline* p, bwtc_cuda_ctx* c) {
       PipeItem& it = *grp[0];
       const void* i1 = it.in;
       void* o1 = it.out;
-      rc = transform_batch(c, &i1, &o1, &it.n, 1, it.starts, it.on_device, it.LF, it.nLF, it.freqs, it.stats);
+      rc = transform_batch(c, &i1, &o1, &it.n, 1, it.starts, it.on_device, it.LF, it.nLF, it.freqs, it.stats, it.runs);
     } else {
       in.resize(cnt); out.resize(cnt); sizes.resize(cnt); nLF.resize(cnt);
       LF.assign((size_t)cnt * 256, 0u);
@@ -1687,10 +1724,10 @@ void pipeline_worker(bwtc_cuda_pipeline* p, bwtc_cuda_ctx* c) {
 }
 
 uint64_t pipeline_enqueue_locked(bwtc_cuda_pipeline* p, const void* in, void* out, uint32_t n, uint32_t starts, bool on_device,
-                                 uint32_t* LF, uint32_t* nLF, uint32_t* freqs, bwtc_cuda_stats* stats) {
+                                 uint32_t* LF, uint32_t* nLF, uint32_t* freqs, bwtc_cuda_stats* stats, bwtc_cuda_runs* runs = nullptr) {
   auto it = std::make_shared<PipeItem>();
   it->in = in; it->out = out; it->n = n; it->starts = starts; it->on_device = on_device;
-  it->LF = LF; it->nLF = nLF; it->freqs = freqs; it->stats = stats;
+  it->LF = LF; it->nLF = nLF; it->freqs = freqs; it->stats = stats; it->runs = runs;
   it->ticket = p->next_ticket++;
   p->queue.push_back(it);
   p->inflight[it->ticket] = it;
@@ -1794,6 +1831,17 @@ int bwtc_cuda_pipeline_submit(bwtc_cuda_pipeline* p, const uint8_t* in, uint8_t*
   {
     std::lock_guard<std::mutex> lk(p->mu);
     *ticket = pipeline_enqueue_locked(p, in, out, n, starts, on_device != 0, LFpowers, nLF, freqs, stats);
+  }
+  p->cv_work.notify_one();
+  return 0;
+}
+
+int bwtc_cuda_pipeline_submit_runs(bwtc_cuda_pipeline* p, const uint8_t* in, uint8_t* out, uint32_t n, uint32_t starts,
+                                   uint32_t* LFpowers, uint32_t* nLF, uint32_t* freqs, bwtc_cuda_runs* runs, uint64_t* ticket) {
+  if (!p || !in || !out || !LFpowers || !nLF || !ticket || n == 0) { if (p) set_err(p->err, "bad arguments"); return BWTC_CUDA_EARG; }
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    *ticket = pipeline_enqueue_locked(p, in, out, n, starts, false, LFpowers, nLF, freqs, nullptr, runs);
   }
   p->cv_work.notify_one();
   return 0;

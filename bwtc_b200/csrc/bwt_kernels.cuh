@@ -1292,7 +1292,7 @@ struct LadderState {
   uint32_t nlog;      // rounds logged below
   uint32_t lists;     // != 0: the lists at `sel` are valid
   uint32_t err;       // copy of ctrl[CTR_ERR] taken by k_finish (so one D2H brings everything back)
-  uint32_t pad;
+  uint32_t nruns;     // run statistics (k_run_emit): maximal runs of equal bytes in the finished output
   uint32_t log_m[LADDER_LOG];     // records processed by ladder round i
   uint32_t log_kind[LADDER_LOG];  // 1 = segmented round, 2 = tail (k_small_rounds: all remaining rounds)
   uint32_t log_h[LADDER_LOG];

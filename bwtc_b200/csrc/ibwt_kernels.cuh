@@ -140,4 +140,88 @@ __global__ void __launch_bounds__(256) k_inv_walk2(const uint32_t* __restrict__ 
   }
 }
 
+// =====================================================================================================
+// Run statistics of the transformed block (the reference's own TODO at HuffmanCoders.cpp:54:
+// "Also gather information about the runs during BWT").  HuffmanEncoder::encodeData re-scans every section of the BWT
+// byte by byte to split it into runs (utils::calculateRunFrequenciesAndStoreRuns, Utils.cpp:150-170).  The device has
+// the bytes in HBM anyway: two streaming kernels emit the maximal runs of the whole block — (symbol, start position)
+// pairs in order — and the host side only slices them at section boundaries.  They are shipped to the host only when
+// they are few (a repetitive block: 5 bytes per run instead of a scan over n bytes); for text-like blocks, where three
+// out of four positions start a run, the scan on the host stays cheaper than the PCIe traffic.
+//   k_run_count : heads per 4096-byte tile (head(i) = i == 0 || out[i] != out[i-1])
+//   (k_scan_tile_counts, the forward path's scan, turns them into exclusive offsets)
+//   k_run_emit  : symbol[off + k] = out[i], start[off + k] = i for the k-th head of the tile
+// =====================================================================================================
+constexpr uint32_t RUN_TILE = 4096;  // bytes per CTA (16 per thread)
+
+__device__ __forceinline__ uint32_t run_heads16(const uint8_t* __restrict__ out, uint32_t n, uint32_t i0, uint8_t* b) {
+  // 16 consecutive bytes of this thread + the byte before them; returns the head mask
+  uint8_t prev = (i0 > 0 && i0 - 1 < n) ? out[i0 - 1] : 0;
+  uint32_t mask = 0;
+  if (i0 + 16 <= n && (reinterpret_cast<uintptr_t>(out + i0) & 15u) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4*>(out + i0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) b[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) b[k] = (i0 + k < n) ? out[i0 + k] : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t i = i0 + k;
+    if (i < n && (i == 0 || b[k] != prev)) mask |= 1u << k;
+    prev = b[k];
+  }
+  return mask;
+}
+
+__global__ void __launch_bounds__(256) k_run_count(const uint8_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ tile_cnt) {
+  __shared__ uint32_t s_w[8];
+  uint8_t b[16];
+  const uint32_t i0 = blockIdx.x * RUN_TILE + threadIdx.x * 16u;
+  uint32_t c = __popc(run_heads16(out, n, i0, b));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    tile_cnt[blockIdx.x] = t;
+  }
+}
+
+// total[0] = number of runs; the arrays are written only while the index stays below `capacity`.
+__global__ void __launch_bounds__(256) k_run_emit(const uint8_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_cnt,
+                                                  const uint32_t* __restrict__ tile_excl, uint32_t ntiles, uint32_t capacity,
+                                                  uint8_t* __restrict__ symbol, uint32_t* __restrict__ start,
+                                                  uint32_t* __restrict__ total) {
+  __shared__ uint32_t s_w[8];
+  uint8_t b[16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t i0 = blockIdx.x * RUN_TILE + threadIdx.x * 16u;
+  const uint32_t mask = run_heads16(out, n, i0, b);
+  const uint32_t c = __popc(mask);
+  uint32_t inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_w[w];
+  uint32_t pos = tile_excl[blockIdx.x] + woff + inc - c;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if ((mask >> k) & 1u) {
+      if (pos < capacity) { symbol[pos] = b[k]; start[pos] = i0 + k; }
+      ++pos;
+    }
+  }
+  if (blockIdx.x == ntiles - 1u && threadIdx.x == 0) total[0] = tile_excl[blockIdx.x] + tile_cnt[blockIdx.x];
+}
+
 }  // namespace bwtc_b200

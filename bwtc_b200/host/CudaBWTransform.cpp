@@ -9,6 +9,7 @@
 #include <string>
 
 #include "bwtc_cuda.h"
+#include "RunStatistics.hpp"
 
 namespace bwtc {
 
@@ -27,6 +28,8 @@ struct Pending {
   uint32 nLF;
   uint32 LF[256];
   uint32 freqs[256];
+  bwtc_cuda_runs runs;            /* run statistics asked for with the block (capacity 0: not asked) */
+  runstats::Record* runRecord;    /* ... land directly in the record that is published when the block is claimed */
 };
 struct Lookahead {
   std::mutex mu;
@@ -98,15 +101,26 @@ void CudaBWTransform::doTransformFused(BWTBlock& block, uint32 *freqs) const {
     const int rc = bwtc_cuda_pipeline_wait(pd->pipe, pd->ticket);
     if (rc < 0) {
       std::string msg = std::string("bwtc::CudaBWTransform: prefetched block failed: ") + bwtc_cuda_pipeline_error(pd->pipe);
+      delete pd->runRecord;
       delete pd;
       throw std::runtime_error(msg);
     }
     if (pd->size != block.size() || pd->nLF != block.LFpowers().size()) {
+      delete pd->runRecord;
       delete pd;
       throw std::runtime_error("bwtc::CudaBWTransform: block changed between prefetch and doTransform");
     }
     for (uint32 j = 0; j < pd->nLF; ++j) block.LFpowers()[j] = pd->LF[j];
     if (freqs) for (int c = 0; c < 256; ++c) freqs[c] += pd->freqs[c];
+    if (pd->runRecord) {
+      if (pd->runs.count != BWTC_CUDA_RUNS_OVERFLOW) {  /* few runs: the coder will not have to scan the block */
+        pd->runRecord->symbol.resize(pd->runs.count);
+        pd->runRecord->start.resize(pd->runs.count);
+        runstats::publish(pd->runRecord);
+      } else {
+        delete pd->runRecord;
+      }
+    }
     delete pd;
     block.setTransformed(true);
     return;
@@ -199,6 +213,7 @@ void CudaBWTransform::shutdownLookahead() {
   std::lock_guard<std::mutex> g(L.mu);
   for (std::map<const byte*, Pending*>::iterator it = L.table.begin(); it != L.table.end(); ++it) {
     bwtc_cuda_pipeline_wait(it->second->pipe, it->second->ticket);  /* the engine still writes into those blocks */
+    delete it->second->runRecord;
     delete it->second;
   }
   L.table.clear();
@@ -239,7 +254,7 @@ void CudaBWTransform::configureLookahead(const std::vector<int>& devices, int de
   L.next = 0;
 }
 
-void CudaBWTransform::prefetch(BWTBlock& block, uint32 startingPoints) {
+void CudaBWTransform::prefetch(BWTBlock& block, uint32 startingPoints, bool wantRunStatistics) {
   Lookahead& L = la();
   std::lock_guard<std::mutex> g(L.mu);
   if (L.pipes.empty() || block.size() == 0 || block.size() > L.maxBlock) return;  /* doTransformFused takes the sync path */
@@ -250,10 +265,30 @@ void CudaBWTransform::prefetch(BWTBlock& block, uint32 startingPoints) {
   pd->size = (uint32)block.size();
   pd->nLF = 0;
   for (int c = 0; c < 256; ++c) pd->freqs[c] = 0;
-  const int rc = bwtc_cuda_pipeline_submit(pd->pipe, block.begin(), block.begin(), pd->size, startingPoints, 0, pd->LF, &pd->nLF,
-                                           pd->freqs, 0, &pd->ticket);
+  pd->runRecord = 0;
+  pd->runs.capacity = 0;
+  int rc;
+  /* run statistics: only for blocks that are transformed on their own (small ones are batched on the device), and only
+   * worth shipping when the block turns out to have few runs — capacity size/8, the engine reports overflow otherwise */
+  if (wantRunStatistics && pd->size > (8u << 20)) {
+    pd->runRecord = new runstats::Record();
+    pd->runRecord->begin = block.begin();
+    pd->runRecord->size = pd->size;
+    pd->runRecord->symbol.resize(pd->size / 8);
+    pd->runRecord->start.resize(pd->size / 8);
+    pd->runs.capacity = pd->size / 8;
+    pd->runs.count = BWTC_CUDA_RUNS_OVERFLOW;
+    pd->runs.symbol = &pd->runRecord->symbol[0];
+    pd->runs.start = &pd->runRecord->start[0];
+    rc = bwtc_cuda_pipeline_submit_runs(pd->pipe, block.begin(), block.begin(), pd->size, startingPoints, pd->LF, &pd->nLF, pd->freqs,
+                                        &pd->runs, &pd->ticket);
+  } else {
+    rc = bwtc_cuda_pipeline_submit(pd->pipe, block.begin(), block.begin(), pd->size, startingPoints, 0, pd->LF, &pd->nLF,
+                                   pd->freqs, 0, &pd->ticket);
+  }
   if (rc < 0) {
     std::string msg = std::string("bwtc::CudaBWTransform::prefetch: ") + bwtc_cuda_pipeline_error(pd->pipe);
+    delete pd->runRecord;
     delete pd;
     throw std::runtime_error(msg);
   }

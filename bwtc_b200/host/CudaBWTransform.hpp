@@ -61,8 +61,10 @@ class CudaBWTransform : public BWTransform {
   static void configureLookahead(const std::vector<int>& devices, int depth, uint32 maxBlockBytes);
   static void shutdownLookahead();
   /* Queues the in-place transform of `block` (sized by startingPoints as BWTManager would).  The block's bytes, the byte
-   * after it excluded, belong to the engine until doTransformFused(block, ...) or cancel. */
-  static void prefetch(BWTBlock& block, uint32 startingPoints);
+   * after it excluded, belong to the engine until doTransformFused(block, ...).  wantRunStatistics: also gather the runs of the
+   * transformed block on the GPU (RunStatistics.hpp; the reference's TODO at HuffmanCoders.cpp:54) — published when the block
+   * is claimed, consumed by the Huffman coder through the wrapped utils::calculateRunFrequenciesAndStoreRuns. */
+  static void prefetch(BWTBlock& block, uint32 startingPoints, bool wantRunStatistics = false);
 
  private:
   void ensure(uint32 block_bytes) const;

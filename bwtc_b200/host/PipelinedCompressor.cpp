@@ -7,6 +7,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -16,6 +17,7 @@
 #include "CudaBWTransform.hpp"
 #include "MemStreams.hpp"
 #include "PrecompressorBlock.hpp"
+#include "RunStatistics.hpp"
 
 namespace bwtc {
 
@@ -87,6 +89,7 @@ void encoderThread(Shared* S, char coderChar, char bwtChoice, uint32 startingPoi
         /* the reference's own per-block entry point (HuffmanCoders.cpp:51-61 / WaveletCoders.cpp:80): BWT through the
          * manager — for choice 'c' a wait for the prefetched block — then header, data, back-patched length */
         coder->transformAndEncode(*job->block, bwtm, &job->out);
+        runstats::release(job->block->begin());  /* run statistics gathered on the GPU for this block, if any */
         busy += since(t0);
         SliceJob* next = job->chain;
         {
@@ -207,6 +210,9 @@ size_t PipelinedCompressor::compress(size_t threads) {
   if(m_precompressor.options().size() == 0) pbBlockSize = bwtBlockSize;
 
   const bool gpu = (m_bwtChoice == 'c');
+  /* GPU run statistics for the Huffman coder (BWTC_RUN_STATS=0 turns them off, e.g. for A/B timing) */
+  const char* rsEnv = getenv("BWTC_RUN_STATS");
+  const bool runStats = gpu && m_options.entropyCoder == 'H' && !(rsEnv && atoi(rsEnv) == 0);
   const size_t gpuSlots = gpu ? std::max<size_t>(1, m_devices.size()) * (size_t)m_depth : 0;
   size_t lookahead = m_lookahead ? m_lookahead : threads + gpuSlots + 2;
   const size_t byBytes = std::max<size_t>(2, (size_t)(8ull << 30) / std::max<size_t>(1, pbBlockSize));
@@ -267,7 +273,7 @@ size_t PipelinedCompressor::compress(size_t threads) {
         sj->owner = pj;
         sj->block = &pb->getSlice((int)i);
         pj->slices.push_back(sj);
-        if (gpu) CudaBWTransform::prefetch(*sj->block, m_startingPoints);  /* in flight on the GPU from now on */
+        if (gpu) CudaBWTransform::prefetch(*sj->block, m_startingPoints, runStats);  /* in flight on the GPU from now on */
       }
       readerBusy += since(t0);
       {

@@ -18,6 +18,8 @@
 #include "CudaBWTransform.hpp"
 #include "MemStreams.hpp"
 #include "PipelinedCompressor.hpp"
+#include "RunStatistics.hpp"
+#include "Utils.hpp"
 
 namespace {
 void put_err(char* err, unsigned errlen, const char* what) {
@@ -191,6 +193,44 @@ long long b200_uncompress_file(const char* in, const char* out) {
   }
   return (long long)sz;
 }
+
+/* Host side of the GPU run statistics (RunStatistics.cpp), checked without a GPU: the maximal runs of data[0..n) are
+ * computed here the plain way and published as the engine would publish them; then every section is asked for through
+ * utils::calculateRunFrequenciesAndStoreRuns (wrapped at link time -> answered from the registry) and through the
+ * reference's real implementation.  Returns 0 if all sections agree (freqs, run symbols, run lengths, counts), the
+ * 1-based index of the first differing section otherwise, -1 if the registry did not answer. */
+extern "C" bwtc::uint64 __real__ZN5utils35calculateRunFrequenciesAndStoreRunsEPmPhPjPKhm(bwtc::uint64*, bwtc::byte*, bwtc::uint32*,
+                                                                                       const bwtc::byte*, size_t);
+int b200_test_run_slicing(const unsigned char* data, unsigned n, const unsigned* section_len, unsigned nsections) {
+  bwtc::runstats::Record* rec = new bwtc::runstats::Record();
+  rec->begin = data;
+  rec->size = n;
+  for (unsigned i = 0; i < n; ++i)
+    if (i == 0 || data[i] != data[i - 1]) { rec->symbol.push_back(data[i]); rec->start.push_back(i); }
+  bwtc::runstats::publish(rec);
+  const size_t served0 = bwtc::runstats::served();
+  std::vector<bwtc::byte> sa(n + 1), sb(n + 1);
+  std::vector<bwtc::uint32> la(n + 1), lb(n + 1);
+  unsigned beg = 0;
+  int bad = 0;
+  for (unsigned s = 0; s < nsections && !bad; ++s) {
+    const unsigned len = section_len[s];
+    if (len == 0) continue;
+    bwtc::uint64 fa[256], fb[256];
+    memset(fa, 0, sizeof fa);
+    memset(fb, 0, sizeof fb);
+    const bwtc::uint64 na = utils::calculateRunFrequenciesAndStoreRuns(fa, &sa[0], &la[0], data + beg, len);
+    const bwtc::uint64 nb = __real__ZN5utils35calculateRunFrequenciesAndStoreRunsEPmPhPjPKhm(fb, &sb[0], &lb[0], data + beg, len);
+    if (na != nb || memcmp(fa, fb, sizeof fa) != 0 || memcmp(&sa[0], &sb[0], na) != 0 || memcmp(&la[0], &lb[0], na * 4) != 0) bad = (int)s + 1;
+    beg += len;
+  }
+  const bool answered = bwtc::runstats::served() > served0;
+  bwtc::runstats::release(data);
+  if (bad) return bad;
+  return answered ? 0 : -1;
+}
+
+size_t b200_run_statistics_served(void) { return bwtc::runstats::served(); }
 
 /* Releases the look-ahead pipelines (device scratch, worker threads) kept between compress() calls. */
 void b200_shutdown(void) { bwtc::CudaBWTransform::shutdownLookahead(); }

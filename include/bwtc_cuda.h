@@ -137,6 +137,25 @@ int64_t bwtc_cuda_bwt_block_device(bwtc_cuda_ctx* ctx, const void* d_in, void* d
 #define BWTC_CUDA_MAX_BATCH 64
 int bwtc_cuda_bwt_blocks(bwtc_cuda_ctx* ctx, void* const* blocks, const uint32_t* sizes, uint32_t count,
                          uint32_t starts, int on_device, uint32_t* LFpowers, uint32_t* nLFpowers, uint32_t* freqs);
+/* ---- run statistics of the transformed block -------------------------------------------- */
+/* The maximal runs of equal bytes of the n output bytes, in order: symbol[k], start[k] (start[0] = 0; run k ends where
+ * run k+1 starts, the last one at n).  This is what HuffmanEncoder::encodeData obtains per section by re-scanning the
+ * block (utils::calculateRunFrequenciesAndStoreRuns, Utils.cpp:150-170; "TODO: Also gather information about the runs
+ * during BWT", HuffmanCoders.cpp:54); the host slices the runs at its section boundaries.  The caller provides the two
+ * arrays and their capacity; if the block has more runs than that, count = BWTC_CUDA_RUNS_OVERFLOW and the arrays are
+ * left alone (text-like blocks have ~0.75 runs per byte: scanning on the host is then cheaper than 5 bytes per run over
+ * PCIe — pass a capacity of n/8 or so and fall back to the scan on overflow). */
+#define BWTC_CUDA_RUNS_OVERFLOW 0xFFFFFFFFu
+typedef struct bwtc_cuda_runs {
+  uint32_t  capacity;  /* in : runs the arrays can hold */
+  uint32_t  count;     /* out: number of runs, or BWTC_CUDA_RUNS_OVERFLOW */
+  uint8_t*  symbol;    /* out: capacity bytes (host) */
+  uint32_t* start;     /* out: capacity words (host) */
+} bwtc_cuda_runs;
+/* bwtc_cuda_bwt_block + the runs of its output. */
+int64_t bwtc_cuda_bwt_block_runs(bwtc_cuda_ctx* ctx, uint8_t* block, uint32_t n, uint32_t* LFpowers, uint32_t nLFpowers,
+                                 uint32_t* freqs, bwtc_cuda_runs* runs);
+
 /* ---- inverse transform: InverseBWTransform::doTransform (InverseBWT.hpp:45-55) ---------------- */
 /* Block level (InverseBWT.cpp:47-51): block holds the n bytes a forward block transform produced, LFpowers its starting
  * points (only LFpowers[0], the end-of-block position, is needed: the device makes its own, far denser samples).  The
@@ -175,6 +194,9 @@ int  bwtc_cuda_pipeline_submit(bwtc_cuda_pipeline* p, const uint8_t* in, uint8_t
                                int on_device, uint32_t* LFpowers, uint32_t* nLF, uint32_t* freqs,
                                bwtc_cuda_stats* stats, uint64_t* ticket);
 int  bwtc_cuda_pipeline_wait(bwtc_cuda_pipeline* p, uint64_t ticket);
+/* submit + run statistics (filled when the block completes; such a block is transformed on its own, not in a batch). */
+int  bwtc_cuda_pipeline_submit_runs(bwtc_cuda_pipeline* p, const uint8_t* in, uint8_t* out, uint32_t n, uint32_t starts,
+                                    uint32_t* LFpowers, uint32_t* nLF, uint32_t* freqs, bwtc_cuda_runs* runs, uint64_t* ticket);
 /* Device-side timing of whatever the pipeline's streams execute between the two calls: begin records
  * an event every context stream waits on; end joins all context streams and returns elapsed ms
  * (CUDA events, all streams of this pipeline), or a negative error. */

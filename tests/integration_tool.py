@@ -58,6 +58,11 @@ def main():
         r = lib.b200_uncompress_file(sys.argv[2].encode(), sys.argv[3].encode())
     else:
         raise SystemExit("unknown op " + op)
+    try:
+        lib.b200_run_statistics_served.restype = ctypes.c_size_t
+        out["run_statistics_served"] = int(lib.b200_run_statistics_served())
+    except AttributeError:
+        pass
     out["rc"] = int(r)
     out["err"] = err.value.decode(errors="replace")
     print(json.dumps(out))
