@@ -225,6 +225,10 @@ def compress_leg(device, nblocks, threads, depth, seed0):
             return 1
         res.append((dt, int(r), list(tm)))
     dt, size, tm = res[-1]
+    try:
+        lib.b200_shutdown()
+    except Exception:  # noqa: BLE001
+        pass
     print(json.dumps({"seconds": dt, "input_bytes": n, "compressed_bytes": size, "encoder_threads": threads, "pipeline_depth": depth,
                       "encoder_busy_core_s": tm[2], "reader_busy_s": tm[1], "writer_busy_s": tm[3], "first_pass_seconds": res[0][0]}))
     return 0
@@ -400,6 +404,34 @@ def main_gpu(args):
     del dev_in, dev_out, page_in, page_out
     torch.cuda.empty_cache()
 
+    # ---- copy-only ceiling of this box at this N: every rank moves 32 MiB pinned buffers in and out concurrently, no
+    # kernels.  The end-to-end figure moves n bytes in and n bytes out per block, so this bounds it from above.
+    ceiling = None
+    try:
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        cb_d = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(4)]
+        cb_e = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(4)]
+        for rep in range(2):
+            barrier()
+            tcp = time.perf_counter()
+            iters = 24
+            for it in range(iters):
+                with torch.cuda.stream(s_in):
+                    cb_d[it % 4].copy_(host_in[it % nb], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    host_out[it % nb].copy_(cb_e[it % 4], non_blocking=True)
+            torch.cuda.synchronize()
+            dtc = time.perf_counter() - tcp
+        tc_t = torch.tensor([dtc], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc_t, op=dist.ReduceOp.MAX)
+        ceiling = {"value": world * iters * n / 1e6 / float(tc_t.item()), "unit": "MB/s per direction, both directions concurrently",
+                   "note": "pinned 32 MiB buffers, two copy streams per GPU, no kernels, max over ranks: the upper bound of `e2e` "
+                           "on this box at this GPU count (host memory / PCIe root)"}
+        del cb_d, cb_e
+    except Exception as e:  # noqa: BLE001
+        ceiling = {"error": str(e)}
+
     # ---- BASELINE config 5 end to end: PipelinedCompressor with CPU Huffman coding overlapped (every rank, own stream)
     comp = None
     if not args.no_compress:
@@ -535,6 +567,7 @@ def main_gpu(args):
                 "e2e_pageable": {"value": page_value, "unit": "MB/s",
                                  "note": "malloc'ed host buffers (what a bwtc PrecompressorBlock is): staged through the engine's "
                                          "pinned ring, memcpy + DMA overlapped on copy streams"},
+                "e2e_copy_ceiling": ceiling,
                 "gpu_launches": int(ltot.item()),
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "configs": configs, "compress_e2e": comp,
                 "wall_ms_per_step": wall_ms_max / args.steps}

@@ -25,7 +25,7 @@ GEN_LIB_PATH = os.path.join(_HERE, "libbwtc_gen.so")
 INTEGRATION_LIB_PATH = os.path.join(_HERE, "libbwtc_integration.so")
 
 MAX_ROUNDS = 40
-MAX_BLOCK = 0x3FFFFFF0            # BWTC_CUDA_MAX_BLOCK
+MAX_BLOCK = 0x7FFFFFFD            # BWTC_CUDA_MAX_BLOCK
 SCRATCH_BYTES_PER_SUFFIX = 40     # BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX
 
 

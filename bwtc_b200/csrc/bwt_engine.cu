@@ -1403,7 +1403,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_aux[1], padded);
 #undef ALLOC
   if (!rc) {  // pad rows of the look-back status: "inclusive prefix = 0", never overwritten
-    std::vector<uint32_t> pad((size_t)LB_PAD_ROWS * 256, LB_PREFIX);
+    std::vector<uint32_t> pad((size_t)LB_PAD_ROWS * 256, LB_PAD_WORD);
     for (int p = 0; p < MAX_PASSES && !rc; ++p) {
       e = cudaMemcpy(c->d_status + (size_t)p * (c->max_rs_tiles + LB_PAD_ROWS) * 256u, pad.data(), pad.size() * 4,
                      cudaMemcpyHostToDevice);

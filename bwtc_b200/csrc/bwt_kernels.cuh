@@ -46,8 +46,11 @@ constexpr int CTR_RERANK = 32;     // [32..47] tile ticket counters of the k_rer
 constexpr int MAX_RERANK_WINDOWS = 16;
 constexpr int CTR_WORDS = 64;
 
-// look-back status words of the radix pass: 2 flag bits + 30-bit count
-constexpr uint32_t LB_AGG = 0x40000000u, LB_PREFIX = 0x80000000u, LB_VALUE = 0x3FFFFFFFu;
+// look-back status words of the radix pass: bit 31 = "inclusive prefix" (else: this tile's count only), bits 30..0 =
+// count + 1, so an unpublished word is simply 0 and counts up to 2^31 - 2 fit — the reference's block limit
+// (Compressor.cpp:78-79) — without a second flag bit.
+constexpr uint32_t LB_PREFIX = 0x80000000u, LB_VALUE = 0x7FFFFFFFu;
+constexpr uint32_t LB_PAD_WORD = LB_PREFIX | 1u;  // "inclusive prefix 0": what the pad rows in front of tile 0 hold
 // Spin watchdog of the look-back loops (a violated dispatch-order assumption becomes an error, not a hang).
 // __constant__ so a test can shrink it (BWTC_DEBUG_SPIN_LIMIT, read by bwtc_cuda_ctx_create).
 __constant__ uint32_t g_lb_spin_limit = 1u << 24;
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(256) k_build_keys(const uint32_t* __restrict__
       if ((livemask >> k) & 1u) {
         // high part = rank >> 1: a live group has >= 2 members, so the heads of two live groups differ by >= 2 and
         // rank >> 1 still identifies (and orders) the group; the dropped bit rides in bit 31 of the id payload
-        // (ids are < 2^30).  One bit less per key is one digit pass less per round at N = 2^k + 1.
+        // (ids are < 2^31).  One bit less per key is one digit pass less per round at N = 2^k + 1.
         const unsigned long long key = ((unsigned long long)(r[k] >> 1) << lo_bits) | (unsigned long long)r2[k];
         keys[pos] = key;
         idx[pos] = (i0 + k) | ((r[k] & 1u) << 31);
@@ -734,7 +737,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(KeyT) == 4 && !AUX) ? BWTC_RS_M
     cnt = run;
     pub = cnt;
     if (tid == 255) pub -= ((uint32_t)TILE - valid);  // pads are not records
-    st_relaxed_u32(my_status, (tile == 0 ? LB_PREFIX : LB_AGG) | pub);
+    st_relaxed_u32(my_status, (tile == 0 ? LB_PREFIX : 0u) | (pub + 1u));
   }
   const uint32_t texcl = scan256_excl(cnt, s_misc + 8);
   const uint32_t gcount = (tid < 256) ? ghist[tid] : 0u;
@@ -780,9 +783,10 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(KeyT) == 4 && !AUX) ? BWTC_RS_M
         int consumed = 0;
 #pragma unroll
         for (int i = 0; i < LB_BATCH; ++i) {
-          const uint32_t isagg = (uint32_t)((int32_t)(v[i] << 1) >> 31);  // bit 30 -> 0 / ~0
-          const uint32_t ispre = (uint32_t)((int32_t)v[i] >> 31);         // bit 31 -> 0 / ~0
-          excl += v[i] & LB_VALUE & alive & (isagg | ispre);
+          const uint32_t pubd = (uint32_t)((int32_t)(v[i] | (0u - v[i])) >> 31);  // published (non-zero) -> ~0
+          const uint32_t ispre = (uint32_t)((int32_t)v[i] >> 31);                 // bit 31 -> 0 / ~0
+          const uint32_t isagg = pubd & ~ispre;
+          excl += ((v[i] & LB_VALUE) - 1u) & alive & pubd;
           fin |= alive & ispre;
           consumed += (int)(alive & isagg & 1u);
           alive &= isagg;
@@ -798,7 +802,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(KeyT) == 4 && !AUX) ? BWTC_RS_M
           __nanosleep(20);
         }
       }
-      st_relaxed_u32(my_status, LB_PREFIX | ((excl + pub) & LB_VALUE));
+      st_relaxed_u32(my_status, LB_PREFIX | ((excl + pub + 1u) & LB_VALUE));
 #ifdef BWTC_PROFILE_STAGES
       if (tid == 0 && g_prof_buf) {
         g_prof_buf[(size_t)tile * 16 + 9] = prof_iters;
@@ -1075,8 +1079,9 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
     aggf = max(aggf, tf);
     aggh = max(aggh, th);
   }
-  // Tile look-back.  One 64-bit word per tile, two independently flagged components:
-  //   [63:62] flagH | [61:32] HH+1 | [31:30] flagF | [29:0] HF+1      (flag 1 = "no head in this tile", 2 = final)
+  // Tile look-back.  One 64-bit word per tile, two independent 32-bit components, [63:32] for HH and [31:0] for HF:
+  //   0 = not published yet, 0xFFFFFFFF = "no head in this tile" (the carry is still being looked up), anything else =
+  //   the final inclusive value (position of the last head + 1, at most 2^31 - 1)
   // A max-scan of positions has a property a sum-scan lacks: a tile that CONTAINS a head already knows its
   // inclusive prefix (its own last head), so it publishes "final" at once and never waits for anybody.  Only
   // a tile whose first record is not a head needs the carry — normally found in the tile right before it —
@@ -1084,48 +1089,49 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
   if (warp == 0) {
     const bool first_is_f = (s_firsthead[0] != 0);          // thread 0's first record is a full-key head
     const bool first_is_h = ROUND0 ? true : (s_firsth0 != 0);
-    const uint32_t pubf = aggf & 0x3FFFFFFFu, pubh = ROUND0 ? 1u : (aggh & 0x3FFFFFFFu);
+    constexpr uint32_t NOHEAD = 0xFFFFFFFFu;
+    constexpr unsigned long long BEFORE_TILE0 = (1ull << 32) | 1ull;  // (never selected: tile 0 always holds a head)
+    const uint32_t pubf = aggf, pubh = ROUND0 ? 1u : aggh;
     const uint32_t flagf = pubf ? 2u : 1u, flagh = pubh ? 2u : 1u;
     uint32_t cf = 0, ch = 0;
     if (lane == 0)
-      st_relaxed_u64(tstate + tile, ((unsigned long long)flagh << 62) | ((unsigned long long)pubh << 32) |
-                                        ((unsigned long long)flagf << 30) | (unsigned long long)pubf);
+      st_relaxed_u64(tstate + tile, ((unsigned long long)(pubh ? pubh : NOHEAD) << 32) | (unsigned long long)(pubf ? pubf : NOHEAD));
     bool needf = !first_is_f && tile > 0, needh = !first_is_h && tile > 0;
     if (needf || needh) {
       long long base = (long long)tile - 1;
       uint32_t spins = 0;
       while (needf || needh) {
         const long long t = base - lane;
-        unsigned long long v = (t >= 0) ? ld_relaxed_u64(tstate + t) : ((2ull << 62) | (2ull << 30));  // before tile 0
-        while ((v >> 62) == 0ull) {                                             // not published yet
+        unsigned long long v = (t >= 0) ? ld_relaxed_u64(tstate + t) : BEFORE_TILE0;
+        while (v == 0ull) {                                                     // not published yet
           ++spins;
           if (spins > g_lb_spin_limit || ((spins & 255u) == 0u && ld_relaxed_u32(ctrl + CTR_ERR))) {
             atomicExch(&ctrl[CTR_ERR], 2u);
-            v = (2ull << 62) | (2ull << 30);
+            v = BEFORE_TILE0;
             break;
           }
           __nanosleep(20);
           v = ld_relaxed_u64(tstate + t);
         }
         if (needf) {
-          const uint32_t fin = __ballot_sync(0xFFFFFFFFu, ((v >> 30) & 3ull) == 2ull);
+          const uint32_t fin = __ballot_sync(0xFFFFFFFFu, (uint32_t)v != NOHEAD);
           if (fin) {
-            cf = __shfl_sync(0xFFFFFFFFu, (uint32_t)(v & 0x3FFFFFFFull), __ffs(fin) - 1);
+            cf = __shfl_sync(0xFFFFFFFFu, (uint32_t)v, __ffs(fin) - 1);
             needf = false;
           }
         }
         if (needh) {
-          const uint32_t fin = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2ull);
+          const uint32_t fin = __ballot_sync(0xFFFFFFFFu, (uint32_t)(v >> 32) != NOHEAD);
           if (fin) {
-            ch = __shfl_sync(0xFFFFFFFFu, (uint32_t)((v >> 32) & 0x3FFFFFFFull), __ffs(fin) - 1);
+            ch = __shfl_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), __ffs(fin) - 1);
             needh = false;
           }
         }
         base -= 32;
       }
       if (lane == 0 && (flagf == 1u || flagh == 1u))  // forward the carry for the component(s) I have no head for
-        st_relaxed_u64(tstate + tile, (2ull << 62) | ((unsigned long long)(flagh == 1u ? ch : pubh) << 32) |
-                                          (2ull << 30) | (unsigned long long)(flagf == 1u ? cf : pubf));
+        st_relaxed_u64(tstate + tile, ((unsigned long long)(flagh == 1u ? ch : pubh) << 32) |
+                                          (unsigned long long)(flagf == 1u ? cf : pubf));
     }
     if (lane == 0) {
       s_cf = cf;

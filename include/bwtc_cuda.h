@@ -37,9 +37,10 @@ extern "C" {
 #define BWTC_CUDA_EINTERNAL (-4)  /* internal consistency check failed (e.g. look-back watchdog) */
 #define BWTC_CUDA_ETOOBIG   (-5)  /* block larger than the context capacity / engine limit */
 
-/* Largest block (bytes, excluding the sentinel slot) the engine accepts: N = n+1 must fit the 30-bit
- * counters of the radix-sort look-back words.  (The reference allows < 2^31-2, Compressor.cpp:78-79.) */
-#define BWTC_CUDA_MAX_BLOCK ((uint32_t)0x3FFFFFF0u)
+/* Largest block (bytes, excluding the sentinel slot) the engine accepts: the reference's own limit — blocks below
+ * 2^31 - 2 bytes (Compressor.cpp:78-79, PrecompressorBlock.cpp:126; N = n + 1 suffixes must index with 31 bits because
+ * LFpowers are serialised as 31-bit values, BWTBlock.cpp:61-86). */
+#define BWTC_CUDA_MAX_BLOCK ((uint32_t)0x7FFFFFFDu)
 
 /* Device scratch per suffix (input, text, output, rank, two key + two id buffers, staged ranks, payload bytes, status
  * words) — an upper bound for blocks of 1 MiB and more; bwtc_cuda_scratch_bytes(n) is the exact figure a context for n-byte blocks allocates. */

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Largest block the engine accepts (BWTC_CUDA_MAX_BLOCK = 0x3FFFFFF0 bytes, N just under 2^30): property check
+"""Largest block the engine accepts (default 0x3FFFFFF0 bytes = 1 GiB; BWTC_CUDA_MAX_BLOCK is 0x7FFFFFFD): property check
 (not a pytest: ~40 GB of device scratch).  python tests/gpu_maxblock.py [KIND] [BYTES]"""
 import os, sys, time
 import numpy as np
