@@ -835,7 +835,7 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
   uint64_t h_next = pl.chars;
   auto sel_of = [](int c) { return (uint32_t)(2 * c) | ((uint32_t)(2 * c + 1) << 4); };
   k_commit_sort<<<1, 1, 0, st>>>(ctx->d_state, ctx->d_ctrl(), (uint32_t)std::min<uint64_t>(h_next, 0x7FFFFFFFull), sel_of(cur),
-                                 0xFFFFFFFFu);
+                                 0xFFFFFFFFu, 1u);
   S.kernel_launches++;
 
   // Concatenate the per-tile chunks k_rerank staged (in d_keys[cur^1]) into compact lists in d_keys[cur], whose
@@ -877,12 +877,16 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
   const uint32_t npassd = div_up((uint64_t)(lo_bits + hi_bits), 8);
   const uint32_t maskd = (1u << npassd) - 1u;
   bool lists_pending = true, first_chunk = true, out_enqueued = false, finished = false;
+  // lean chunk: behind a global radix round whose groups were still far above the segmented-round limit nothing sort-free
+  // is enqueued speculatively (it would only be skipped on the device): commit, k_finish (error word), state copy, wait
+  bool lean = false;
+  constexpr uint32_t LEAN_MAXGROUP = 8u * SEG_MAXGROUP;
   uint32_t nlog_seen = 0;
   const uint32_t dbg = ctx->debug_max_rounds;
   for (;;) {
     // ---- one ladder chunk: [lists] [K x (segmented round, rank update, commit)] [tail] [finish] [copies]
-    const bool chunk_built_lists = lists_pending;
-    if (!(dbg && S.rounds >= dbg)) {
+    const bool chunk_built_lists = lists_pending && !lean;
+    if (!(dbg && S.rounds >= dbg) && !lean) {
       if (lists_pending) {
         if (make_lists(true)) return BWTC_CUDA_ECUDA;
         lists_pending = false;
@@ -969,6 +973,20 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
     first_chunk = false;
     if (H.m == 0) { finished = true; break; }
     out_enqueued = false;  // the speculative copies ran before the block was complete: repeat them at the end
+    if (lean) {
+      lean = false;
+      if (H.m <= (uint32_t)SMALL_MAX || (ctx->use_seg && H.maxgroup <= (uint32_t)SEG_MAXGROUP)) {
+        // the groups collapsed after all: build the lists now and run a normal ladder chunk
+        if (make_lists(false)) return BWTC_CUDA_ECUDA;
+        k_mark_lists<<<1, 1, 0, st>>>(ctx->d_state, sel_of(cur));
+        CK(ctx, cudaGetLastError());
+        S.kernel_launches++;
+        S.algorithmic_bytes += (uint64_t)H.m * 16;
+        lists_pending = false;
+        m_bound = H.m;
+        continue;
+      }
+    }
     if (dbg && S.rounds >= dbg) break;
     const uint32_t m = H.m;
     m_bound = m;
@@ -1036,7 +1054,8 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
       S.algorithmic_bytes += (uint64_t)m * 12 + (uint64_t)m * 4;
     }
     h_next = std::min<uint64_t>((uint64_t)h32 * 2, 0x7FFFFFFFull);
-    k_commit_sort<<<1, 1, 0, st>>>(ctx->d_state, ctx->d_ctrl(), (uint32_t)h_next, sel_of(cur), expect_cursor);
+    lean = !dbg && H.maxgroup > LEAN_MAXGROUP;  // (group sizes before this round; they rarely drop 8x in one)
+    k_commit_sort<<<1, 1, 0, st>>>(ctx->d_state, ctx->d_ctrl(), (uint32_t)h_next, sel_of(cur), expect_cursor, lean ? 0u : 1u);
     CK(ctx, cudaGetLastError());
     S.kernel_launches++;
     if (r < BWTC_CUDA_MAX_ROUNDS) {
@@ -1207,8 +1226,8 @@ int64_t run_inverse(bwtc_cuda_ctx* ctx, bool block_mode, const uint8_t* h_in, ui
   uint32_t* distA = nxtA + Sn;
   uint32_t* nxtB = distA + Sn;
   uint32_t* distB = nxtB + Sn;
-  uint32_t* len = distB + Sn;  // 5 * ceil(N / 128) <= N words for N >= 8; tiny blocks: d_scat has N + 16 words
-  if ((uint64_t)5 * Sn > (uint64_t)N + 16) {  // N < ~8: use the (idle) second id buffer as well
+  uint32_t* len = distB + Sn;  // 5 * ceil(N / INV_K) words fit d_scat (N + 16 words) unless N is tiny
+  if ((uint64_t)5 * Sn > (uint64_t)N + 16) {  // tiny N: use the (idle) second id / key buffers as well
     nxtA = ctx->d_idx[cur ^ 1]; distA = nxtA + Sn; nxtB = ctx->d_scat; distB = nxtB + Sn; len = static_cast<uint32_t*>(ctx->d_keys[1]);
   }
   const uint32_t sgrid = div_up(Sn, 256);
@@ -1379,6 +1398,16 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   } while (0)
   int sm = 0;
   if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sm > 0) c->sm_count = sm;
+  {  // refuse up front, with a clear message, what the device cannot hold (instead of failing half way through the list)
+    size_t free_b = 0, total_b = 0;
+    const uint64_t need = bwtc_cuda_scratch_bytes(max_block_bytes);
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need > (uint64_t)free_b) {
+      set_err(g_err, "a context for %u-byte blocks needs %llu bytes of device memory, %llu are free", max_block_bytes,
+              (unsigned long long)need, (unsigned long long)free_b);
+      delete c;
+      return BWTC_CUDA_EALLOC;
+    }
+  }
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { set_err(g_err, "cudaStreamCreate: %s", cudaGetErrorString(e)); rc = BWTC_CUDA_ECUDA; }
   const size_t padded = ((N + TEXT_PAD + 15) / 16) * 16 + 16;

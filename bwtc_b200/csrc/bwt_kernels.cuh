@@ -1323,7 +1323,8 @@ __device__ __forceinline__ void ladder_free_slots(uint32_t sel, int* f) {
 
 // After a sort round: take the re-rank's totals, name the place the lists WILL be in (k_gather_chunks builds them
 // only if the next step consumes them), clear the accumulators for the segmented rounds.
-__global__ void k_commit_sort(LadderState* st, uint32_t* ctrl, uint32_t h_new, uint32_t sel_lists, uint32_t expect_cursor) {
+__global__ void k_commit_sort(LadderState* st, uint32_t* ctrl, uint32_t h_new, uint32_t sel_lists, uint32_t expect_cursor,
+                              uint32_t will_build_lists) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   // k_build_keys must have emitted exactly the records the previous round left live (0xFFFFFFFF: no such check)
   if (expect_cursor != 0xFFFFFFFFu && ctrl[CTR_CURSOR] != expect_cursor && !ctrl[CTR_ERR]) ctrl[CTR_ERR] = 5u;
@@ -1332,10 +1333,17 @@ __global__ void k_commit_sort(LadderState* st, uint32_t* ctrl, uint32_t h_new, u
   st->maxgroup = g;
   st->h = h_new;
   st->sel = sel_lists;
-  st->lists = ladder_wants_lists(m, g) ? 1u : 0u;
+  st->lists = (will_build_lists && ladder_wants_lists(m, g)) ? 1u : 0u;  // (k_gather_chunks follows only if will_build_lists)
   ctrl[CTR_LIVE] = 0;
   ctrl[CTR_MAXGROUP] = 0;
   ctrl[CTR_UPD] = 0;
+}
+
+// The host built the lists unconditionally (make_lists(false)) behind a lean chunk: tell the ladder kernels.
+__global__ void k_mark_lists(LadderState* st, uint32_t sel_lists) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->sel = sel_lists;
+  st->lists = 1u;
 }
 
 // After k_seg_round + k_apply_ranks.

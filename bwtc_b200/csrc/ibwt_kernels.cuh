@@ -11,7 +11,7 @@
 //   2. k_radix_pass   x 2 (the forward path's one-sweep LSD pass, stable): Psi[g] = the L-row of F-row g, i.e. the
 //                     rank of the suffix that starts one position LATER in T' — walking Psi walks T' forwards
 //   3. k_inv_ctable   C[c] = number of key values < c (F[g] is recovered by a search in C, no F array in memory)
-//   4. k_inv_walk1    every K-th rank is a SPLITTER; each splitter follows Psi to the next splitter: (next, length)
+//   4. k_inv_walk1    every K-th rank (K = 32) is a SPLITTER; each splitter follows Psi to the next splitter: (next, length)
 //   5. k_inv_jump     x ceil(log2 S): pointer jumping over the S = N/K splitters -> distance of each to the end of the
 //                     cycle opened at rank 0 (suffix N-1), i.e. its text position
 //   6. k_inv_walk2    each splitter walks its stretch again and writes X[n-1-q] = F[rank(q)] for its text positions q
@@ -23,7 +23,12 @@
 
 namespace bwtc_b200 {
 
-constexpr uint32_t INV_K = 128;          // splitter spacing in rank space (average chain length)
+#ifndef BWTC_INV_K
+#define BWTC_INV_K 32
+#endif
+constexpr uint32_t INV_K = BWTC_INV_K;   // splitter spacing in rank space = average chain length.  Measured (32 MiB Markov, one
+                                         // block): 128 -> 2.63 ms, 64 -> 2.29 ms, 32 -> 2.00 ms: shorter chains even out the
+                                         // geometric spread of chain lengths that leaves lanes idle (profiles/r02_summary.md)
 constexpr uint32_t INV_NIL = 0xFFFFFFFFu;
 
 // key[r] = L[r] + 1, 0 at the sentinel row.  Row N-1 holds, in the block contract, the byte the forward transform

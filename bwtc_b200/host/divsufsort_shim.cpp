@@ -11,33 +11,39 @@
  */
 #include <cstdio>
 #include <cstdlib>
-#include <mutex>
 
 #include "../../include/bwtc_cuda.h"
 
 namespace {
-std::mutex g_mu;
-bwtc_cuda_ctx* g_ctx = 0;
-uint32_t g_cap = 0;
+/* One context per calling thread (created on first use, regrown for larger blocks, released when the thread ends): callers
+ * on different threads — e.g. the encoder threads of a parallel compressor — do not serialise on each other. */
+struct ThreadCtx {
+  bwtc_cuda_ctx* ctx;
+  uint32_t cap;
+  ThreadCtx() : ctx(0), cap(0) {}
+  ~ThreadCtx() { if (ctx) bwtc_cuda_ctx_destroy(ctx); }
+};
+thread_local ThreadCtx t_ctx;
 
 bwtc_cuda_ctx* ctx_for(uint32_t n) {
-  if (g_ctx && n <= g_cap) return g_ctx;
+  ThreadCtx& t = t_ctx;
+  if (t.ctx && n <= t.cap) return t.ctx;
   uint64_t want = n;
-  if (g_ctx) {
-    want = (uint64_t)g_cap * 2 > want ? (uint64_t)g_cap * 2 : want;
-    bwtc_cuda_ctx_destroy(g_ctx);
-    g_ctx = 0;
+  if (t.ctx) {
+    want = (uint64_t)t.cap * 2 > want ? (uint64_t)t.cap * 2 : want;
+    bwtc_cuda_ctx_destroy(t.ctx);
+    t.ctx = 0;
   }
   if (want < (1u << 20)) want = 1u << 20;
   if (want > BWTC_CUDA_MAX_BLOCK) want = BWTC_CUDA_MAX_BLOCK;
   const char* dev = getenv("BWTC_CUDA_DEVICE");
-  int rc = bwtc_cuda_ctx_create(&g_ctx, dev ? atoi(dev) : 0, (uint32_t)want);
+  int rc = bwtc_cuda_ctx_create(&t.ctx, dev ? atoi(dev) : 0, (uint32_t)want);
   if (rc != 0) {
     fprintf(stderr, "bwtc_b200 divsufsort shim: cannot create CUDA context (%d): %s\n", rc, bwtc_cuda_global_error());
     abort();
   }
-  g_cap = (uint32_t)want;
-  return g_ctx;
+  t.cap = (uint32_t)want;
+  return t.ctx;
 }
 }  // namespace
 
@@ -49,7 +55,6 @@ int32_t divbwtf(const uint8_t* T, uint8_t* U, int32_t* A, int32_t n, unsigned* L
   (void)A;
   if (T == 0 || U == 0 || n < 0) return -1;           /* divsufsort.c:488 */
   if (n <= 1) { if (n == 1) U[0] = T[0]; return n; }  /* divsufsort.c:489 */
-  std::lock_guard<std::mutex> lock(g_mu);
   bwtc_cuda_ctx* c = ctx_for((uint32_t)n);
   int64_t rc = bwtc_cuda_divbwtf(c, T, U, (uint32_t)n, LFpowers, nLFpowers, freqs);
   if (rc < 0) {

@@ -68,6 +68,47 @@ int b200_base_wrapper_block(unsigned char* buf, unsigned n, unsigned starts, cha
   } catch (const std::exception& e) { put_err(err, errlen, e.what()); return -1; }
 }
 
+/* A manager / transformer that lives across blocks, as Compressor's m_bwtmanager does (Compressor.hpp:118): what the
+ * per-block throughput of options B and C is measured with (the one-shot entry points above build and destroy the
+ * CUDA context per call). */
+void* b200_manager_new(char choice, unsigned starts) {
+  try {
+    bwtc::BWTManager* m = new bwtc::BWTManager();
+    m->setStartingPoints(starts);
+    m->initialize(choice);
+    return m;
+  } catch (...) { return 0; }
+}
+void b200_manager_free(void* h) { delete static_cast<bwtc::BWTManager*>(h); }
+int b200_manager_transform(void* h, unsigned char* buf, unsigned n, unsigned* LF_out, unsigned* nLF_out, unsigned* freqs, char* err,
+                           unsigned errlen) {
+  try {
+    bwtc::BWTBlock b(buf, n, false);
+    static_cast<bwtc::BWTManager*>(h)->doTransform(b, freqs);
+    *nLF_out = (unsigned)b.LFpowers().size();
+    for (size_t i = 0; i < b.LFpowers().size(); ++i) LF_out[i] = b.LFpowers()[i];
+    return 0;
+  } catch (const std::exception& e) { put_err(err, errlen, e.what()); return -1; }
+}
+void* b200_transformer_new(char choice) {
+  try { return bwtc::giveTransformer(choice); } catch (...) { return 0; }
+}
+void b200_transformer_free(void* h) { delete static_cast<bwtc::BWTransform*>(h); }
+/* the NON-virtual base wrapper (host std::reverse, BWTransform.cpp:52-64) on a transformer that is kept */
+int b200_transformer_base_wrapper(void* h, unsigned char* buf, unsigned n, unsigned starts, unsigned* LF_out, unsigned* nLF_out,
+                                  unsigned* freqs, char* err, unsigned errlen) {
+  try {
+    bwtc::BWTManager sizing;
+    sizing.setStartingPoints(starts);
+    bwtc::BWTBlock b(buf, n, false);
+    b.prepareLFpowers(sizing.getStartingPoints());
+    static_cast<bwtc::BWTransform*>(h)->doTransform(b, freqs);
+    *nLF_out = (unsigned)b.LFpowers().size();
+    for (size_t i = 0; i < b.LFpowers().size(); ++i) LF_out[i] = b.LFpowers()[i];
+    return 0;
+  } catch (const std::exception& e) { put_err(err, errlen, e.what()); return -1; }
+}
+
 /* giveTransformer(choice)->doTransform(T, N, LF[, freqs]): the raw virtual on a caller-prepared buffer, as the
  * reference's tests call it (test/InverseBwtTest.cpp:57-66). */
 int b200_transformer_raw(unsigned char* T, unsigned N, unsigned nLF, char choice, unsigned* LF_out, unsigned* freqs, char* err,

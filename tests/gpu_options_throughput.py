@@ -23,11 +23,21 @@ def child(mode, nblocks):
                               ctypes.c_void_p(LF.ctypes.data), ctypes.byref(k), ctypes.c_void_p(fr.ctypes.data))
     else:
         lib = ctypes.CDLL(bw.INTEGRATION_LIB_PATH)
-        fn = lib.b200_base_wrapper_block if mode == "B" else lib.b200_manager_block
-        def run(b):
-            rc = fn(ctypes.c_void_p(b.ctypes.data), ctypes.c_uint(n), ctypes.c_uint(8), ctypes.c_char(b"c"), ctypes.c_void_p(LF.ctypes.data),
-                    ctypes.byref(k), ctypes.c_void_p(fr.ctypes.data), err, ctypes.c_uint(512))
-            assert rc == 0, err.value
+        lib.b200_manager_new.restype = ctypes.c_void_p
+        lib.b200_transformer_new.restype = ctypes.c_void_p
+        if mode == "B":  # a transformer kept across blocks, the reference's non-virtual base wrapper around its raw virtual
+            h = ctypes.c_void_p(lib.b200_transformer_new(ctypes.c_char(b"c")))
+            def run(b):
+                rc = lib.b200_transformer_base_wrapper(h, ctypes.c_void_p(b.ctypes.data), ctypes.c_uint(n), ctypes.c_uint(8),
+                                                       ctypes.c_void_p(LF.ctypes.data), ctypes.byref(k), ctypes.c_void_p(fr.ctypes.data),
+                                                       err, ctypes.c_uint(512))
+                assert rc == 0, err.value
+        else:            # the patched BWTManager kept across blocks, as Compressor's m_bwtmanager is
+            h = ctypes.c_void_p(lib.b200_manager_new(ctypes.c_char(b"c"), ctypes.c_uint(8)))
+            def run(b):
+                rc = lib.b200_manager_transform(h, ctypes.c_void_p(b.ctypes.data), ctypes.c_uint(n), ctypes.c_void_p(LF.ctypes.data),
+                                                ctypes.byref(k), ctypes.c_void_p(fr.ctypes.data), err, ctypes.c_uint(512))
+                assert rc == 0, err.value
     run(blocks[0].copy())  # warm-up: context creation
     t0 = time.perf_counter()
     for b in blocks:
