@@ -27,6 +27,7 @@ INTEGRATION_LIB_PATH = os.path.join(_HERE, "libbwtc_integration.so")
 MAX_ROUNDS = 40
 MAX_BLOCK = 0x7FFFFFFD            # BWTC_CUDA_MAX_BLOCK
 SCRATCH_BYTES_PER_SUFFIX = 40     # BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX
+SCRATCH_FIXED_BYTES = 8 << 20     # BWTC_CUDA_SCRATCH_FIXED_BYTES
 
 
 class BwtcCudaUnavailable(RuntimeError):
@@ -348,8 +349,8 @@ class CudaBWTransform:
 
     def maxBlockSize(self, memory_budget: int) -> int:
         """Largest block whose scratch fits the budget (BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX = 40 is an upper bound from
-        1 MiB on; the fixed part is ~3 MiB)."""
-        b = max(0, (memory_budget - (3 << 20)) // SCRATCH_BYTES_PER_SUFFIX - 1)
+        1 MiB on; the fixed part is below 8 MiB)."""
+        b = max(0, (memory_budget - SCRATCH_FIXED_BYTES) // SCRATCH_BYTES_PER_SUFFIX - 1)
         return min(b, MAX_BLOCK)
 
     def suggestedBlockSize(self, memory_budget: int) -> int:

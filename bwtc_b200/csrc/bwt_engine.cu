@@ -61,6 +61,7 @@ constexpr uint32_t LF_PARK = MAX_BATCH * 256, LF_WORDS = LF_PARK + MAX_BATCH + 8
 // their own.  Pinned caller buffers are copied directly.
 constexpr size_t RING_CHUNK = 4u << 20;
 constexpr int RING_SLOTS = 4;
+constexpr uint32_t KTAB_BITS = 20;  // lazy ranks: prefix table of the sorted round-0 keys (4 MiB)
 
 struct bwtc_cuda_ctx {
   int device = 0;
@@ -94,6 +95,10 @@ struct bwtc_cuda_ctx {
                                   // then [max_aux_tiles][MAX_RERANK_WINDOWS+1] bucket offsets of the bucketed scatter
   uint32_t* d_LF = nullptr;       // [LF_PARK) LFpowers (one row of 256 per block of a batch), [LF_PARK + k] parked hole byte
                                   // of block k
+  uint32_t* d_livebits = nullptr; // lazy ranks: bit i = rank[i] is stored (N / 32 words)
+  uint32_t* d_ktab = nullptr;     // lazy ranks: first sorted position per key prefix ((1 << KTAB_BITS) + 2 words)
+  LookupParams* d_lookup = nullptr;  // ... what rank_lookup needs, in device memory
+  LookupParams* h_lookup = nullptr;  // (pinned host copy)
   LadderState* d_state = nullptr; // device-side round control (bwt_kernels.cuh)
   LadderState* h_state = nullptr; // ... its pinned host copy
   unsigned long long* d_wtab = nullptr;  // window-sample table: WS_SLOTS keys, WS_SLOTS counters, 2 doubles
@@ -114,6 +119,10 @@ struct bwtc_cuda_ctx {
   int debug_fake_watchdog = 0;    // test hook: pretend the watchdog fired while static tile ids are in use
   int debug_reverse_tiles = 0;    // test hook: static tile ids in REVERSE dispatch order (a real violation)
   int ladder_first = 2, ladder_more = 4;  // segmented rounds enqueued speculatively behind a sort round / per retry
+  int use_lazy = 1;               // lazy ranks after round 0: 0 never, 1 when a sample of the sorted keys says
+                                  // few suffixes stay in groups, 2 always (tests)
+  uint32_t lazy_min_suffixes = 4u << 20;
+  double lazy_max_live = 0.025;
   int use_seg = 1;                // segmented (sort-free) doubling rounds when every group is small
   int use_batch = 1;              // small equal-sized blocks of one call are sorted as one text
   int use_pack_pred = 1;          // carry code(T[id-1]) above the id through the round-0 sort when it fits
@@ -123,6 +132,7 @@ struct bwtc_cuda_ctx {
   uint32_t force_chars = 0, force_keybytes = 0;
   uint32_t debug_max_rounds = 0;  // != 0: stop refining after this many rounds (results are then wrong on purpose)
   int last_cur = 0;               // sort buffer holding the last round's sorted records
+  RerankParams rr0;               // round-0 re-rank parameters of the block in flight (fallback out of lazy ranks)
   bwtc_cuda_stats stats;
   char err[512];
   uint32_t* d_ctrl() const { return d_zero; }
@@ -160,7 +170,8 @@ void ctx_free(bwtc_cuda_ctx* c) {
   cudaFree(c->d_keys[0]); cudaFree(c->d_keys[1]); cudaFree(c->d_idx[0]); cudaFree(c->d_idx[1]);
   cudaFree(c->d_zero); cudaFree(c->d_status); cudaFree(c->d_LF); cudaFree(c->d_wtab); cudaFree(c->d_tilecnt); cudaFree(c->d_scat);
   cudaFree(c->d_bhist); cudaFree(c->d_bptr); cudaFree(c->d_aux[0]); cudaFree(c->d_aux[1]);
-  cudaFree(c->d_state);
+  cudaFree(c->d_state); cudaFree(c->d_livebits); cudaFree(c->d_ktab); cudaFree(c->d_lookup);
+  if (c->h_lookup) cudaFreeHost(c->h_lookup);
   if (c->h_batch) cudaFreeHost(c->h_batch);
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->h_state) cudaFreeHost(c->h_state);
@@ -181,6 +192,8 @@ void ctx_free(bwtc_cuda_ctx* c) {
 struct Round0Plan {
   uint32_t sigma, bits, chars, keybytes, npass;
   PackParams pp;
+  bool has_memory;    // the 8-gram sample says the source is not i.i.d.-like (text, repeats)
+  double live_pred;   // i.i.d.-like sources: predicted fraction of suffixes still tied after round 0, L(chars)
 };
 
 // Dense alphabet + round-0 key shape.  present[c] != 0 for every byte of the text.
@@ -244,6 +257,17 @@ void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* pr
       keybytes = ((uint64_t)chars * b + blk_bits <= 32) ? 4 : 8;
     }
   }
+  pl->has_memory = true;
+  pl->live_pred = 1.0;
+  if (!(ctx->force_chars || ctx->force_keybytes)) {
+    double q2 = 0.0;
+    for (int c = 0; c < 256; ++c)
+      if (present[c] && count[c]) { const double q = (double)count[c] / total; q2 += q * q; }
+    const double samples = pair_stats[1];
+    const double expected = samples * (samples - 1.0) * 0.5 * std::pow(q2, 8.0);
+    pl->has_memory = (H0 < 1e-3) || samples < 64.0 || (pair_stats[0] > 8.0 * expected + 16.0);
+    if (!pl->has_memory) pl->live_pred = 1.0 - std::exp(-(double)N * std::exp2(-H0 * (double)chars));
+  }
   pl->sigma = sigma;
   pl->bits = b;
   pl->chars = chars;
@@ -270,6 +294,8 @@ uint32_t rerank_launches(const bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m) {
   const uint32_t w = rerank_windows(ctx, N, m);
   return (ctx->bucket_min_windows && w >= (uint32_t)ctx->bucket_min_windows) ? 1u : w;
 }
+
+inline bool dbg_any(const bwtc_cuda_ctx* ctx) { return ctx->debug_max_rounds != 0; }
 
 // Tile-id source of the look-back kernels: the block index (default), tickets, or the reversed debug map.
 inline uint32_t tile_slot(const bwtc_cuda_ctx* ctx, uint32_t ticket_word) {
@@ -370,10 +396,10 @@ int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m, uint32_t rs_til
 // as fast (measured) and needs no staging.
 template <typename KeyT, bool ROUND0>
 int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankParams rp, const EmitParams& ep,
-                  uint32_t* stage_nr, uint32_t* stage_id) {
+                  uint32_t* stage_nr, uint32_t* stage_id, bool single_window = false, bool no_stage = false) {
   cudaStream_t st = ctx->stream;
   const uint32_t tiles = div_up(m, AUX_TILE);
-  const uint32_t nwin = rerank_windows(ctx, N, m);
+  const uint32_t nwin = single_window ? 1u : rerank_windows(ctx, N, m);
   const KeyT* keys = static_cast<const KeyT*>(ctx->d_keys[cur]);
   uint32_t* woff = ctx->d_tilecnt + 2 * ctx->max_aux_tiles;
   if (ctx->bucket_min_windows && nwin >= (uint32_t)ctx->bucket_min_windows) {
@@ -383,8 +409,11 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
     rp.ctr_slot = tile_slot(ctx, (uint32_t)CTR_RERANK);
     rp.nbuckets = nwin;
     rp.bucket_magic = (uint32_t)(((1ull << 32) + win_ids - 1) / win_ids);
-    StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, 1, ctx->d_idx[cur ^ 1], ctx->d_scat, woff};
-    k_rerank<KeyT, ROUND0><<<tiles, 256, 0, st>>>(keys, ctx->d_idx[cur], ctx->d_rank, rp, ctx->d_tstate(), ctx->d_ctrl(), ep, sp);
+    StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, no_stage ? 0 : 1, ctx->d_idx[cur ^ 1], ctx->d_scat, woff};
+    if (ROUND0 && rp.lazy)
+      k_rerank<KeyT, ROUND0, ROUND0><<<tiles, 256, 0, st>>>(keys, ctx->d_idx[cur], ctx->d_rank, rp, ctx->d_tstate(), ctx->d_ctrl(), ep, sp);
+    else
+      k_rerank<KeyT, ROUND0><<<tiles, 256, 0, st>>>(keys, ctx->d_idx[cur], ctx->d_rank, rp, ctx->d_tstate(), ctx->d_ctrl(), ep, sp);
     const uint32_t grid = std::min<uint32_t>(div_up(tiles, 8), (uint32_t)ctx->sm_count * 8u);
     for (uint32_t b = 0; b < nwin; ++b)
       k_scatter_bucket<<<grid, 256, 0, st>>>(ctx->d_idx[cur ^ 1], ctx->d_scat, woff, tiles, nwin, b, AUX_TILE, ctx->d_rank, ctx->d_ctrl());
@@ -399,9 +428,13 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
     rp.ctr_slot = tile_slot(ctx, (uint32_t)(CTR_RERANK + w));
     rp.nbuckets = 0;
     rp.bucket_magic = 0;
-    StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, w == 0 ? 1 : 0, nullptr, nullptr, nullptr};
-    k_rerank<KeyT, ROUND0><<<tiles, 256, 0, st>>>(keys, ctx->d_idx[cur], ctx->d_rank, rp,
-                                                   ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl(), ep, sp);
+    StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, (w == 0 && !no_stage) ? 1 : 0, nullptr, nullptr, nullptr};
+    if (ROUND0 && rp.lazy)
+      k_rerank<KeyT, ROUND0, ROUND0><<<tiles, 256, 0, st>>>(keys, ctx->d_idx[cur], ctx->d_rank, rp,
+                                                            ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl(), ep, sp);
+    else
+      k_rerank<KeyT, ROUND0><<<tiles, 256, 0, st>>>(keys, ctx->d_idx[cur], ctx->d_rank, rp,
+                                                     ctx->d_tstate() + (size_t)w * ctx->max_aux_tiles, ctx->d_ctrl(), ep, sp);
     CK(ctx, cudaGetLastError());
     ctx->stats.kernel_launches++;
   }
@@ -799,6 +832,23 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
   S.passes[0] = pdone;
   S.prefix_len[0] = 0;
   S.rounds = 1;
+  // ---- lazy ranks?  The rank scatter of round 0 — a random 4-byte write per suffix — is 20-35% of a block,
+  // but after round 0 only the ranks of suffixes that are still in a group are ever refined, and a singleton's rank is simply
+  // its position in the sorted key array.  If a sample of the sorted keys says few suffixes stay in groups, rank[] is
+  // written for those only and the others are looked up in the retained sorted keys when needed (rank_lookup).
+  bool lazy = false;
+  const uint32_t keybits0 = pl.chars * pl.bits;
+  if (ctx->use_lazy && !bs && !dbg_any(ctx) && N >= 64 && keybits0 >= 1) {
+    // The decision needs no measurement: for an i.i.d.-like source (DNA, random bytes) the key-shape policy has already
+    // predicted the fraction of suffixes still tied after round 0, L(c) = 1 - exp(-N 2^(-H0 c)) — it matches the measured
+    // live fractions to three digits (DNA 64 MiB: 0.0156 / 0.0155; random 256 MiB: 0.0606 / 0.0606).  Lazy ranks pay a
+    // search per looked-up rank (~0.1 us each), so they win only when few ranks are looked up: measured -15% on the DNA
+    // 64 MiB block (1.5% live), break-even at ~8% (Markov text), a loss at 6% on 256 MiB blocks whose sorted keys are far
+    // larger than L2 (profiles/r02_experiments.md).  A wrong prediction only costs time: the fallback below is exact.
+    lazy = ctx->use_lazy >= 2 || (!pl.has_memory && pl.live_pred <= ctx->lazy_max_live && N >= ctx->lazy_min_suffixes);
+  }
+  const uint32_t tbits = std::min<uint32_t>(KTAB_BITS, keybits0);
+  const uint32_t lazy_cap = N / 6;  // the lists of lazy mode live in six slices of d_scat
   {
     RerankParams rp;
     rp.m = N;
@@ -807,7 +857,28 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
       rp.short_thresh = pl.chars > text_end ? 0u : text_end - pl.chars + 1u;
     }
     rp.lo_bits = 0;
-    S.flags = (ctx->static_tiles ? 0u : 1u) | (bs ? 2u : 0u) | (pack_pred ? 4u : 0u) | (aux_pred ? 8u : 0u);
+    rp.lazy = lazy ? 1u : 0u;
+    rp.livebits = ctx->d_livebits;
+    rp.ktab = ctx->d_ktab;
+    rp.tshift = keybits0 - tbits;
+    if (lazy) {
+      CK(ctx, cudaMemsetAsync(ctx->d_livebits, 0, ((size_t)N / 32 + 4) * 4, st));
+      CK(ctx, cudaMemsetAsync(ctx->d_ktab, 0xFF, ((size_t)(1u << tbits) + 2) * 4, st));
+      LookupParams& L = *ctx->h_lookup;
+      L.enabled = 1;
+      L.keybytes = pl.keybytes;
+      L.sorted_keys = ctx->d_keys[cur];
+      L.ktab = ctx->d_ktab;
+      L.livebits = ctx->d_livebits;
+      L.text = d_text;
+      L.N = N;
+      L.bits = pl.bits;
+      L.chars = pl.chars;
+      L.tshift = keybits0 - tbits;
+      memcpy(L.lut, pl.pp.lut, 256);
+      CK(ctx, cudaMemcpyAsync(ctx->d_lookup, ctx->h_lookup, sizeof(LookupParams), cudaMemcpyHostToDevice, st));
+    }
+    S.flags = (ctx->static_tiles ? 0u : 1u) | (bs ? 2u : 0u) | (pack_pred ? 4u : 0u) | (aux_pred ? 8u : 0u) | (lazy ? 16u : 0u);
     rp.packed = pack_pred ? 1u : (aux_pred ? 2u : 0u);
     rp.pred_aux = ctx->d_aux[cur];
     rp.id_bits = pack_pred ? id_bits : 31u;
@@ -816,10 +887,19 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
     for (int c = 0; c < 256; ++c)
       if (J.present[c]) rp.decode[pl.pp.lut[c]] = (uint8_t)c;
     uint32_t* snr = reinterpret_cast<uint32_t*>(ctx->d_keys[cur ^ 1]);
-    if (pl.keybytes == 4) rc = launch_rerank<uint32_t, true>(ctx, cur, N, N, rp, ep, snr, snr + N);
-    else rc = launch_rerank<unsigned long long, true>(ctx, cur, N, N, rp, ep, snr, snr + N);
+    if (pl.keybytes == 4) rc = launch_rerank<uint32_t, true>(ctx, cur, N, N, rp, ep, snr, snr + N, lazy);
+    else rc = launch_rerank<unsigned long long, true>(ctx, cur, N, N, rp, ep, snr, snr + N, lazy);
     if (rc) return rc;
-    S.algorithmic_bytes += (uint64_t)N * (pl.keybytes + 4) + (uint64_t)N * 4;
+    S.algorithmic_bytes += (uint64_t)N * (pl.keybytes + 4) + (lazy ? 0ull : (uint64_t)N * 4);
+    if (lazy) {
+      const uint32_t entries = 1u << tbits, nchunks = div_up(entries, KTAB_CHUNK);
+      uint32_t* cmin = ctx->d_bhist;  // <= 256 words of the (idle) per-block histogram area
+      k_ktab_chunkmin<<<nchunks, 256, 0, st>>>(ctx->d_ktab, entries, cmin);
+      k_ktab_fill<<<nchunks, 256, 0, st>>>(ctx->d_ktab, entries, N, cmin, nchunks);
+      CK(ctx, cudaGetLastError());
+      S.kernel_launches += 2;
+    }
+    ctx->rr0 = rp;  // (kept for the fallback out of lazy mode)
   }
   // six u32[N] work arrays: halves of the two key buffers and the two id buffers
   PoolPtrs pool;
@@ -829,13 +909,18 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
   pool.p[3] = reinterpret_cast<uint32_t*>(ctx->d_keys[1]) + N;
   pool.p[4] = ctx->d_idx[0];
   pool.p[5] = ctx->d_idx[1];
+  const PoolPtrs norm = pool;  // (the staging slots of k_rerank are always halves of the idle key buffer)
+  if (lazy) {  // the sorted keys (d_keys[cur]) must survive: lists, next lists and rank updates live in six slices of d_scat
+    for (int q = 0; q < 6; ++q) pool.p[q] = ctx->d_scat + (size_t)q * lazy_cap;
+  }
+  const LookupParams* lkp = lazy ? ctx->d_lookup : nullptr;
   ctx->last_cur = cur;
   uint32_t m_prev = N;       // records of the last global sort = extent of the k_rerank staging slots
   uint32_t m_bound = N;      // upper bound of the live count (it never grows)
   uint64_t h_next = pl.chars;
-  auto sel_of = [](int c) { return (uint32_t)(2 * c) | ((uint32_t)(2 * c + 1) << 4); };
+  auto sel_of = [&lazy](int c) { return lazy ? 0x10u : ((uint32_t)(2 * c) | ((uint32_t)(2 * c + 1) << 4)); };
   k_commit_sort<<<1, 1, 0, st>>>(ctx->d_state, ctx->d_ctrl(), (uint32_t)std::min<uint64_t>(h_next, 0x7FFFFFFFull), sel_of(cur),
-                                 0xFFFFFFFFu, 1u);
+                                 0xFFFFFFFFu, 1u, lazy ? lazy_cap : 0xFFFFFFFFu);
   S.kernel_launches++;
 
   // Concatenate the per-tile chunks k_rerank staged (in d_keys[cur^1]) into compact lists in d_keys[cur], whose
@@ -844,9 +929,10 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
   auto make_lists = [&](bool speculative) -> int {
     const uint32_t tiles = div_up(m_prev, AUX_TILE);
     k_scan_tile_counts<<<1, 1024, 0, st>>>(ctx->d_tilecnt, ctx->d_tilecnt + ctx->max_aux_tiles, tiles);
-    k_gather_chunks<<<tiles, 256, 0, st>>>(pool.p[2 * (cur ^ 1)], pool.p[2 * (cur ^ 1) + 1], ctx->d_tilecnt,
-                                           ctx->d_tilecnt + ctx->max_aux_tiles, AUX_TILE, pool.p[2 * cur], pool.p[2 * cur + 1],
-                                           speculative ? ctx->d_state : nullptr, ctx->d_ctrl());
+    k_gather_chunks<<<tiles, 256, 0, st>>>(norm.p[2 * (cur ^ 1)], norm.p[2 * (cur ^ 1) + 1], ctx->d_tilecnt,
+                                           ctx->d_tilecnt + ctx->max_aux_tiles, AUX_TILE, lazy ? pool.p[0] : norm.p[2 * cur],
+                                           lazy ? pool.p[1] : norm.p[2 * cur + 1], speculative ? ctx->d_state : nullptr,
+                                           ctx->d_ctrl());
     CK(ctx, cudaGetLastError());
     S.kernel_launches += 2;
     return 0;
@@ -896,13 +982,14 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
         // persistent grid; the first round behind a sort is the big one, later (often skipped) ones get a leaner grid
         const uint32_t per_sm = (k == 0) ? 12u : 4u;
         const uint32_t seg_grid = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(m_bound, SEG_T), (uint32_t)ctx->sm_count * per_sm));
-        k_seg_round<<<seg_grid, 256, 0, st>>>(ctx->d_state, pool, ctx->d_rank, N, ep, ctx->d_ctrl());
+        if (lkp) k_seg_round<true><<<seg_grid, 256, 0, st>>>(ctx->d_state, pool, ctx->d_rank, N, ep, ctx->d_ctrl(), lkp);
+        else k_seg_round<false><<<seg_grid, 256, 0, st>>>(ctx->d_state, pool, ctx->d_rank, N, ep, ctx->d_ctrl(), nullptr);
         k_apply_ranks<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_state, pool, ctx->d_ctrl(), ctx->d_rank);
         k_commit_seg<<<1, 1, 0, st>>>(ctx->d_state, ctx->d_ctrl());
         S.kernel_launches += 3;
       }
       if (!dbg) {
-        k_small_rounds<<<1, 1024, 0, st>>>(ctx->d_state, pool, ctx->d_rank, N, ep, ctx->d_ctrl());
+        k_small_rounds<<<1, 1024, 0, st>>>(ctx->d_state, pool, ctx->d_rank, N, ep, ctx->d_ctrl(), lkp);
         S.kernel_launches++;
       }
       CK(ctx, cudaGetLastError());
@@ -913,7 +1000,7 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
                                                   ctx->d_LF + LF_PARK, ctx->d_state, ctx->d_ctrl());
     else
       k_finish<<<1, 256, 0, st>>>(ctx->d_rank, d_text, N, J.d_dst, J.block_mode ? 1 : 0, ctx->d_LF, J.nLF, ctx->d_LF + LF_PARK,
-                                  ctx->d_state, ctx->d_ctrl());
+                                  ctx->d_state, ctx->d_ctrl(), lkp);
     CK(ctx, cudaGetLastError());
     S.kernel_launches++;
     if (J.runs && !bs && J.block_mode) {
@@ -923,9 +1010,10 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
       uint32_t* rcnt = ctx->d_status + (size_t)LB_PAD_ROWS * 256u;
       uint32_t* rexcl = rcnt + rtiles;
       const uint32_t cap_dev = std::min<uint32_t>(J.runs->capacity, n);
-      k_run_count<<<rtiles, 256, 0, st>>>(J.d_dst, n, rcnt);
+      k_run_count<<<rtiles, 256, 0, st>>>(J.d_dst, n, rcnt, ctx->d_state);
       k_scan_tile_counts<<<1, 1024, 0, st>>>(rcnt, rexcl, rtiles);
-      k_run_emit<<<rtiles, 256, 0, st>>>(J.d_dst, n, rcnt, rexcl, rtiles, cap_dev, ctx->d_aux[0], ctx->d_scat, &ctx->d_state->nruns);
+      k_run_emit<<<rtiles, 256, 0, st>>>(J.d_dst, n, rcnt, rexcl, rtiles, cap_dev, ctx->d_aux[0], ctx->d_scat, &ctx->d_state->nruns,
+                                         ctx->d_state);
       CK(ctx, cudaGetLastError());
       S.kernel_launches += 3;
       S.algorithmic_bytes += 2ull * n;
@@ -973,6 +1061,26 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
     first_chunk = false;
     if (H.m == 0) { finished = true; break; }
     out_enqueued = false;  // the speculative copies ran before the block was complete: repeat them at the end
+    if (lazy && !H.lists) {
+      // Out of lazy mode: more suffixes stayed in groups than the small list pool holds, or groups are large (a global
+      // radix round scans rank[] in text order and needs every rank).  Materialise the singletons' ranks from the sorted
+      // records of round 0 (still intact), then carry on with the full-rank path; nothing else has run in between.
+      RerankParams rp = ctx->rr0;
+      rp.lazy = 2u;
+      CK(ctx, cudaMemsetAsync(ctx->d_tstate(), 0, (size_t)rerank_launches(ctx, N, N) * ctx->max_aux_tiles * 8, st));
+      CK(ctx, cudaMemsetAsync(ctx->d_ctrl() + CTR_PASS0, 0, (size_t)(CTR_WORDS - CTR_PASS0) * 4, st));  // tile tickets
+      uint32_t* snr = reinterpret_cast<uint32_t*>(ctx->d_keys[cur ^ 1]);
+      lazy = false;  // (sel_of and the pools below now mean the full-rank layout)
+      if (pl.keybytes == 4) rc = launch_rerank<uint32_t, true>(ctx, cur, N, N, rp, ep, snr, snr + N, false, true);
+      else rc = launch_rerank<unsigned long long, true>(ctx, cur, N, N, rp, ep, snr, snr + N, false, true);
+      if (rc) return rc;
+      S.algorithmic_bytes += (uint64_t)N * (pl.keybytes + 4) + (uint64_t)N * 4;
+      S.flags |= 32u;  // lazy ranks were abandoned for this block
+      pool = norm;
+      lkp = nullptr;
+      lean = true;  // the lists (if the next step wants them) are built below from the intact staging
+      lists_pending = true;
+    }
     if (lean) {
       lean = false;
       if (H.m <= (uint32_t)SMALL_MAX || (ctx->use_seg && H.maxgroup <= (uint32_t)SEG_MAXGROUP)) {
@@ -1055,7 +1163,8 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
     }
     h_next = std::min<uint64_t>((uint64_t)h32 * 2, 0x7FFFFFFFull);
     lean = !dbg && H.maxgroup > LEAN_MAXGROUP;  // (group sizes before this round; they rarely drop 8x in one)
-    k_commit_sort<<<1, 1, 0, st>>>(ctx->d_state, ctx->d_ctrl(), (uint32_t)h_next, sel_of(cur), expect_cursor, lean ? 0u : 1u);
+    k_commit_sort<<<1, 1, 0, st>>>(ctx->d_state, ctx->d_ctrl(), (uint32_t)h_next, sel_of(cur), expect_cursor, lean ? 0u : 1u,
+                                   0xFFFFFFFFu);
     CK(ctx, cudaGetLastError());
     S.kernel_launches++;
     if (r < BWTC_CUDA_MAX_ROUNDS) {
@@ -1373,6 +1482,9 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (const char* e = getenv("BWTC_POLL_SLEEP_US")) c->poll_sleep_us = std::max(1, atoi(e));
   if (const char* e = getenv("BWTC_LADDER_FIRST")) c->ladder_first = std::max(0, atoi(e));
   if (const char* e = getenv("BWTC_LADDER_MORE")) c->ladder_more = std::max(1, atoi(e));
+  if (const char* e = getenv("BWTC_LAZY")) c->use_lazy = atoi(e);
+  if (const char* e = getenv("BWTC_LAZY_MIN_MIB")) c->lazy_min_suffixes = (uint32_t)std::max(0L, atol(e)) << 20;
+  if (const char* e = getenv("BWTC_LAZY_MAX_LIVE")) c->lazy_max_live = atof(e);
   if (const char* e = getenv("BWTC_SEG")) c->use_seg = atoi(e);
   if (const char* e = getenv("BWTC_BATCH")) c->use_batch = atoi(e);
   if (const char* e = getenv("BWTC_PACK_PRED")) c->use_pack_pred = atoi(e);
@@ -1423,6 +1535,9 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_status, (size_t)MAX_PASSES * (c->max_rs_tiles + LB_PAD_ROWS) * 1024u);
   ALLOC(c->d_LF, (size_t)LF_WORDS * 4);
   ALLOC(c->d_state, sizeof(LadderState));
+  ALLOC(c->d_livebits, (N / 32 + 4) * 4);
+  ALLOC(c->d_ktab, ((size_t)(1u << KTAB_BITS) + 2) * 4);
+  ALLOC(c->d_lookup, sizeof(LookupParams));
   ALLOC(c->d_bhist, (size_t)MAX_BATCH * 256 * 4);
   ALLOC(c->d_bptr, (size_t)MAX_BATCH * sizeof(void*));
   ALLOC(c->d_wtab, (size_t)WS_SLOTS * 12 + 64);
@@ -1443,6 +1558,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
     e = cudaMallocHost((void**)&c->h_small, (size_t)(CTR_WORDS + HIST_WORDS + 256 + 8) * 4);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_batch, (size_t)MAX_BATCH * (sizeof(void*) + 2 * 256 * 4));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_state, sizeof(LadderState));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_lookup, sizeof(LookupParams));
     if (e != cudaSuccess) { set_err(g_err, "cudaMallocHost: %s", cudaGetErrorString(e)); rc = BWTC_CUDA_EALLOC; }
   }
   if (!rc && (cudaEventCreate(&c->ev_begin) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess ||
@@ -1500,6 +1616,7 @@ uint64_t bwtc_cuda_scratch_bytes(uint32_t max_block_bytes) {
   b += (uint64_t)LF_WORDS * 4 + sizeof(LadderState) + (uint64_t)MAX_BATCH * 256 * 4 + (uint64_t)MAX_BATCH * sizeof(void*);
   b += (uint64_t)WS_SLOTS * 12 + 64;                        // d_wtab
   b += aux_tiles * (2 + MAX_RERANK_WINDOWS + 1) * 4 + 64;   // d_tilecnt
+  b += (N / 32 + 4) * 4 + ((uint64_t)(1u << KTAB_BITS) + 2) * 4 + sizeof(LookupParams);  // lazy ranks: d_livebits, d_ktab, d_lookup
   return b;
 }
 

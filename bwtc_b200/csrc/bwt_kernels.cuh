@@ -863,7 +863,128 @@ struct RerankParams {
   uint8_t decode[256];      // dense code -> byte (packed emission)
   uint32_t nbuckets;        // > 1: bucketed scatter — instead of writing rank[] the tile stages its (id, rank) pairs
   uint32_t bucket_magic;    //      grouped by id bucket (bucket = min(umulhi(id, magic), nbuckets-1)); see k_scatter_bucket
+  // ROUND0, lazy ranks: 1 = rank[] is written only for suffixes that stay in a group (and the few "short"
+  // ones), their bit is set in livebits, and the first sorted position of every key prefix goes to ktab; a singleton's
+  // rank is its sorted position and is looked up in the retained sorted keys when somebody needs it (rank_lookup).
+  // 2 = materialise: write rank[] for the singletons only (the fallback out of lazy mode; nothing else is touched).
+  uint32_t lazy;
+  uint32_t* livebits;
+  uint32_t* ktab;
+  uint32_t tshift;          // key >> tshift = table index
 };
+
+// What a consumer of ranks needs in lazy mode (by value in the kernel arguments).
+struct LookupParams {
+  uint32_t enabled;          // 0: rank[] is complete, plain loads
+  uint32_t keybytes;         // 4 or 8: type of the sorted round-0 keys
+  const void* sorted_keys;   // N keys in sorted order
+  const uint32_t* ktab;      // (1 << tbits) + 1 entries: first sorted position whose key prefix is >= the index
+  const uint32_t* livebits;  // bit i set: rank[i] is valid
+  const uint8_t* text;
+  uint32_t N, bits, chars, tshift;
+  uint8_t lut[256];
+};
+
+// rank of suffix j (without the DONE flag).
+__device__ __forceinline__ uint32_t rank_lookup(const LookupParams& lk, const uint32_t* __restrict__ rank, uint32_t j) {
+  if (!lk.enabled || ((lk.livebits[j >> 5] >> (j & 31u)) & 1u)) return rank[j] & RANK_MASK;
+  unsigned long long key = 0;  // the round-0 key of suffix j, as k_pack_round0 builds it
+  for (uint32_t c = 0; c < lk.chars; ++c) {
+    const uint32_t g = j + c;
+    key = (key << lk.bits) | (unsigned long long)((g < lk.N) ? lk.lut[lk.text[g]] : 0u);
+  }
+  const uint32_t p = (uint32_t)(key >> lk.tshift);
+  uint32_t lo = lk.ktab[p], hi = lk.ktab[p + 1u];
+  if (lk.keybytes == 8u) {
+    const unsigned long long* sk = static_cast<const unsigned long long*>(lk.sorted_keys);
+    while (lo < hi) {  // lower bound: the key is unique (singleton), so this is its position
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (sk[mid] < key) lo = mid + 1u; else hi = mid;
+    }
+  } else {
+    const uint32_t* sk = static_cast<const uint32_t*>(lk.sorted_keys);
+    const uint32_t k32 = (uint32_t)key;
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (sk[mid] < k32) lo = mid + 1u; else hi = mid;
+    }
+  }
+  return lo;
+}
+
+// ktab holds the first sorted position of every key prefix that occurs (k_rerank, lazy) and 0xFFFFFFFF elsewhere; fill the
+// holes from the right (suffix minimum) so that [ktab[p], ktab[p+1]) is the position range of prefix p.  ktab[entries] = N.
+// Two small kernels over chunks of KTAB_CHUNK entries: chunk minima, then every chunk takes the minimum of the chunks to
+// its right as its carry and fills itself.  (A single-CTA sweep over the 2^20 entries took 0.6 ms.)
+constexpr uint32_t KTAB_CHUNK = 4096;  // 256 threads x 16
+
+__global__ void __launch_bounds__(256) k_ktab_chunkmin(const uint32_t* __restrict__ ktab, uint32_t entries, uint32_t* __restrict__ cmin) {
+  __shared__ uint32_t s_w[8];
+  const uint32_t base = blockIdx.x * KTAB_CHUNK + threadIdx.x * 16u;
+  uint32_t mn = 0xFFFFFFFFu;
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (base + k < entries) mn = min(mn, ktab[base + k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0xFFFFFFFFu;
+    for (int w = 0; w < 8; ++w) t = min(t, s_w[w]);
+    cmin[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ktab_fill(uint32_t* __restrict__ ktab, uint32_t entries, uint32_t N,
+                                                   const uint32_t* __restrict__ cmin, uint32_t nchunks) {
+  __shared__ uint32_t s_w[8];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // carry = first position of any prefix in the chunks to the right (N if none)
+  uint32_t c = N;
+  for (uint32_t q = blockIdx.x + 1u + tid; q < nchunks; q += 256) c = min(c, cmin[q]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(0xFFFFFFFFu, c, o));
+  if (lane == 0) s_w[warp] = c;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t t = N;
+    for (int w = 0; w < 8; ++w) t = min(t, s_w[w]);
+    s_carry = t;
+    if (blockIdx.x == nchunks - 1u) ktab[entries] = N;
+  }
+  __syncthreads();
+  const uint32_t carry = s_carry;
+  // thread tid owns 16 entries; thread 255 the highest.  Suffix minimum: from the right.
+  const uint32_t base = blockIdx.x * KTAB_CHUNK + (uint32_t)tid * 16u;
+  uint32_t v[16];
+  uint32_t mn = 0xFFFFFFFFu;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    v[k] = (base + k < entries) ? ktab[base + k] : 0xFFFFFFFFu;
+    mn = min(mn, v[k]);
+  }
+  // exclusive suffix-min over threads: min of the threads to my right
+  uint32_t inc = mn;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_down_sync(0xFFFFFFFFu, inc, o);
+    if (lane + o < 32) inc = min(inc, t);
+  }
+  __syncthreads();
+  if (lane == 0) s_w[warp] = inc;
+  uint32_t ex = __shfl_down_sync(0xFFFFFFFFu, inc, 1);
+  if (lane == 31) ex = 0xFFFFFFFFu;
+  __syncthreads();
+  for (int w = warp + 1; w < 8; ++w) ex = min(ex, s_w[w]);
+  uint32_t run = min(ex, carry);
+#pragma unroll
+  for (int k = 15; k >= 0; --k) {
+    run = min(run, v[k]);
+    if (base + k < entries) ktab[base + k] = run;
+  }
+}
 
 // Live-record staging of k_rerank.  The window launch with sp.enable != 0 writes, for EVERY record of its tile
 // that stays in a non-singleton group (whatever its id window), the pair (new rank, id) in sorted order to
@@ -917,8 +1038,8 @@ __device__ __forceinline__ void emit_bwt(const EmitParams& ep, uint32_t nr, uint
   else ep.out[nr] = ch;
 }
 
-template <typename KeyT, bool ROUND0>
-__global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx,
+template <typename KeyT, bool ROUND0, bool LAZY = false>
+__global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const KeyT* __restrict__ keys, const uint32_t* __restrict__ idx,
                                                 uint32_t* __restrict__ rank, RerankParams rp,
                                                 unsigned long long* __restrict__ tstate,
                                                 uint32_t* __restrict__ ctrl, EmitParams ep, StageParams sp) {
@@ -1177,7 +1298,7 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
         changed = (HF != HH);
       }
       const bool in_win = (id[k] >= rp.win_lo) && (id[k] < rp.win_hi);
-      if (single && in_win && !owns_hole(ep, id[k])) {  // emit L[nr] = T[id-1]
+      if (single && in_win && !owns_hole(ep, id[k]) && !(LAZY && rp.lazy == 2u)) {  // emit L[nr] = T[id-1]
         uint8_t ch;
         if (ROUND0 && rp.packed) ch = s_dec[((k < 4 ? pc0 >> (8 * k) : pc1 >> (8 * (k - 4)))) & 0xFFu];
         else ch = ep.text[id[k] - 1];
@@ -1186,7 +1307,22 @@ __global__ void __launch_bounds__(256, ROUND0 ? 5 : 4) k_rerank(const KeyT* __re
       if (single) nr |= RANK_DONE;
       else if (sp.enable) { ++live; livemask |= 1u << k; gmax = max(gmax, j - HF + 1u); }
       nrv[k] = nr;
-      if (in_win && (changed || single)) {
+      bool wr = in_win && (changed || single);
+      if (LAZY && rp.lazy) {
+        const bool isshort = id[k] >= rp.short_thresh;
+        if (rp.lazy == 1u) {
+          wr = in_win && (!single || isshort);  // a singleton's rank is its sorted position: not stored (rank_lookup)
+          if (wr) atomicOr(&rp.livebits[id[k] >> 5], 1u << (id[k] & 31u));
+          // first sorted position of every key prefix
+          const uint32_t pfx = (uint32_t)(key[k] >> rp.tshift);
+          const bool firstrec = (k == 0 && !has_prev);
+          const uint32_t ppfx = firstrec ? 0xFFFFFFFFu : (uint32_t)(((k == 0) ? prevkey : key[k - 1]) >> rp.tshift);
+          if (firstrec || pfx != ppfx) rp.ktab[pfx] = j;
+        } else {
+          wr = in_win && single && !isshort;    // materialise the singletons (everything else is in place)
+        }
+      }
+      if (wr) {
         if (bucketed) {
           const uint32_t b = min(__umulhi(id[k], rp.bucket_magic), rp.nbuckets - 1u);
           bpos[k] = atomicAdd(&s_bcnt[b], 1u);
@@ -1299,6 +1435,7 @@ struct LadderState {
   uint32_t lists;     // != 0: the lists at `sel` are valid
   uint32_t err;       // copy of ctrl[CTR_ERR] taken by k_finish (so one D2H brings everything back)
   uint32_t nruns;     // run statistics (k_run_emit): maximal runs of equal bytes in the finished output
+  uint32_t pad2[4];
   uint32_t log_m[LADDER_LOG];     // records processed by ladder round i
   uint32_t log_kind[LADDER_LOG];  // 1 = segmented round, 2 = tail (k_small_rounds: all remaining rounds)
   uint32_t log_h[LADDER_LOG];
@@ -1324,7 +1461,7 @@ __device__ __forceinline__ void ladder_free_slots(uint32_t sel, int* f) {
 // After a sort round: take the re-rank's totals, name the place the lists WILL be in (k_gather_chunks builds them
 // only if the next step consumes them), clear the accumulators for the segmented rounds.
 __global__ void k_commit_sort(LadderState* st, uint32_t* ctrl, uint32_t h_new, uint32_t sel_lists, uint32_t expect_cursor,
-                              uint32_t will_build_lists) {
+                              uint32_t will_build_lists, uint32_t list_capacity) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   // k_build_keys must have emitted exactly the records the previous round left live (0xFFFFFFFF: no such check)
   if (expect_cursor != 0xFFFFFFFFu && ctrl[CTR_CURSOR] != expect_cursor && !ctrl[CTR_ERR]) ctrl[CTR_ERR] = 5u;
@@ -1333,7 +1470,9 @@ __global__ void k_commit_sort(LadderState* st, uint32_t* ctrl, uint32_t h_new, u
   st->maxgroup = g;
   st->h = h_new;
   st->sel = sel_lists;
-  st->lists = (will_build_lists && ladder_wants_lists(m, g)) ? 1u : 0u;  // (k_gather_chunks follows only if will_build_lists)
+  // (k_gather_chunks follows only if will_build_lists; lazy ranks keep the lists in a smaller pool: if the live records do
+  // not fit, nothing is built and the host falls back to the full path)
+  st->lists = (will_build_lists && m <= list_capacity && ladder_wants_lists(m, g)) ? 1u : 0u;
   ctrl[CTR_LIVE] = 0;
   ctrl[CTR_MAXGROUP] = 0;
   ctrl[CTR_UPD] = 0;
@@ -1472,9 +1611,10 @@ __global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restr
 
 // Persistent grid: tile t = blockIdx.x, blockIdx.x + gridDim.x, ... while t * SEG_T < m (m is read from the
 // device-side LadderState, so the host can enqueue the round before it knows how many suffixes are live).
+template <bool LAZY>
 __global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const LadderState* __restrict__ st, PoolPtrs pool,
                                                    const uint32_t* __restrict__ rank, uint32_t N, EmitParams ep,
-                                                   uint32_t* __restrict__ ctrl) {
+                                                   uint32_t* __restrict__ ctrl, const LookupParams* __restrict__ lkp) {
   constexpr int IPT = SEG_CAP / 256;
   __shared__ unsigned long long s_key[SEG_CAP];
   __shared__ uint32_t s_id[SEG_CAP];
@@ -1551,10 +1691,18 @@ __global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const LadderSt
   for (int w = 0; w < 8; ++w) { const uint32_t t = s_wa[w]; if (w < warp) woff += t; L += t; }
   {
     uint32_t lo[IPT];
+    if (!LAZY) {
 #pragma unroll
-    for (int k = 0; k < IPT; ++k) {  // independent gathers first (all in flight together), shared-memory writes after
-      lo[k] = 0;
-      if (((livemask >> k) & 1u) && h < N - myid[k]) lo[k] = (rank[myid[k] + h] & RANK_MASK) + 1u;
+      for (int k = 0; k < IPT; ++k) {  // independent gathers first (all in flight together), shared-memory writes after
+        lo[k] = 0;
+        if (((livemask >> k) & 1u) && h < N - myid[k]) lo[k] = (rank[myid[k] + h] & RANK_MASK) + 1u;
+      }
+    } else {  // lazy ranks: a singleton's rank is found in the sorted round-0 keys (LookupParams live in global memory)
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        lo[k] = 0;
+        if (((livemask >> k) & 1u) && h < N - myid[k]) lo[k] = rank_lookup(*lkp, rank, myid[k] + h) + 1u;
+      }
     }
     uint32_t pos = woff + inc - cnt;
 #pragma unroll
@@ -1749,7 +1897,8 @@ __global__ void __launch_bounds__(256) k_apply_ranks(const LadderState* __restri
 // Replaces the tail of trsort's loop (trsort.c:563-585), where only a few groups are left.
 // =====================================================================================================
 __global__ void __launch_bounds__(1024) k_small_rounds(LadderState* st, PoolPtrs pool, uint32_t* rank,
-                                                       uint32_t N, EmitParams ep, uint32_t* __restrict__ ctrl) {
+                                                       uint32_t N, EmitParams ep, uint32_t* __restrict__ ctrl,
+                                                       const LookupParams* __restrict__ lkp) {
   __shared__ unsigned long long s_key[SMALL_MAX];
   __shared__ uint32_t s_id[SMALL_MAX];
   __shared__ uint32_t s_a[32], s_b[32];
@@ -1780,8 +1929,10 @@ __global__ void __launch_bounds__(1024) k_small_rounds(LadderState* st, PoolPtrs
       unsigned long long key = ~0ull;  // pads sort last
       if (j < m) {
         const uint32_t i = s_id[j];
-        const uint32_t hi = rank[i] & RANK_MASK;
-        const uint32_t lo = (h < (unsigned long long)(N - i)) ? ((rank[i + (uint32_t)h] & RANK_MASK) + 1u) : 0u;
+        const uint32_t hi = rank[i] & RANK_MASK;  // (i is live: its rank is always stored)
+        uint32_t lo = 0u;
+        if (h < (unsigned long long)(N - i))
+          lo = (lkp ? rank_lookup(*lkp, rank, i + (uint32_t)h) : (rank[i + (uint32_t)h] & RANK_MASK)) + 1u;
         key = ((unsigned long long)hi << 32) | lo;
       }
       s_key[j] = key;
@@ -1888,16 +2039,16 @@ __global__ void __launch_bounds__(256) k_finish(const uint32_t* __restrict__ ran
                                                 uint32_t N, uint8_t* __restrict__ out, int block_mode,
                                                 uint32_t* __restrict__ LF, uint32_t nLF,
                                                 const uint32_t* __restrict__ lastch, LadderState* st,
-                                                const uint32_t* __restrict__ ctrl) {
-  const uint32_t pidx = rank[0] & RANK_MASK;
+                                                const uint32_t* __restrict__ ctrl, const LookupParams* __restrict__ lkp) {
   const uint32_t tid = threadIdx.x;
   const uint32_t err = ctrl[CTR_ERR];
   if (tid == 0) st->err = err;
   if (err || st->m != 0u) return;  // failed (rank[] is not trustworthy), or refinement not finished yet: the host
                                    // continues and launches k_finish again
+  const uint32_t pidx = lkp ? rank_lookup(*lkp, rank, 0u) : (rank[0] & RANK_MASK);
   if (tid < nLF) {
     const uint32_t x = N / nLF;
-    LF[tid] = (tid == 0) ? pidx : (rank[N - tid * x] & RANK_MASK);
+    LF[tid] = (tid == 0) ? pidx : (lkp ? rank_lookup(*lkp, rank, N - tid * x) : (rank[N - tid * x] & RANK_MASK));
   }
   if (tid == 0) {
     if (block_mode) {

@@ -181,8 +181,10 @@ __device__ __forceinline__ uint32_t run_heads16(const uint8_t* __restrict__ out,
   return mask;
 }
 
-__global__ void __launch_bounds__(256) k_run_count(const uint8_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ tile_cnt) {
+__global__ void __launch_bounds__(256) k_run_count(const uint8_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ tile_cnt,
+                                                   const LadderState* __restrict__ st) {
   __shared__ uint32_t s_w[8];
+  if (st->m != 0u) return;  // enqueued speculatively behind the ladder: the block is not finished yet
   uint8_t b[16];
   const uint32_t i0 = blockIdx.x * RUN_TILE + threadIdx.x * 16u;
   uint32_t c = __popc(run_heads16(out, n, i0, b));
@@ -201,8 +203,9 @@ __global__ void __launch_bounds__(256) k_run_count(const uint8_t* __restrict__ o
 __global__ void __launch_bounds__(256) k_run_emit(const uint8_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_cnt,
                                                   const uint32_t* __restrict__ tile_excl, uint32_t ntiles, uint32_t capacity,
                                                   uint8_t* __restrict__ symbol, uint32_t* __restrict__ start,
-                                                  uint32_t* __restrict__ total) {
+                                                  uint32_t* __restrict__ total, const LadderState* __restrict__ st) {
   __shared__ uint32_t s_w[8];
+  if (st->m != 0u) return;
   uint8_t b[16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t i0 = blockIdx.x * RUN_TILE + threadIdx.x * 16u;

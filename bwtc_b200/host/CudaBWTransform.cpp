@@ -164,8 +164,8 @@ uint64 CudaBWTransform::maxSizeInBytes(uint64 block_size) const {
   return bwtc_cuda_scratch_bytes((uint32)(block_size > BWTC_CUDA_MAX_BLOCK ? BWTC_CUDA_MAX_BLOCK : block_size));
 }
 uint64 CudaBWTransform::maxBlockSize(uint64 memory_budget) const {
-  if (memory_budget <= (3u << 20) + 64) return 0;
-  uint64 b = (memory_budget - (3u << 20)) / BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX - 1;
+  if (memory_budget <= BWTC_CUDA_SCRATCH_FIXED_BYTES + 64) return 0;
+  uint64 b = (memory_budget - BWTC_CUDA_SCRATCH_FIXED_BYTES) / BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX - 1;
   return b > BWTC_CUDA_MAX_BLOCK ? BWTC_CUDA_MAX_BLOCK : b;
 }
 uint64 CudaBWTransform::suggestedBlockSize(uint64 memory_budget) const {
@@ -181,8 +181,8 @@ CudaInverseBWTransform::~CudaInverseBWTransform() {
 }
 
 uint64 CudaInverseBWTransform::maxBlockSize(uint64 memory_budget) const {
-  if (memory_budget <= (3u << 20) + 64) return 0;
-  uint64 b = (memory_budget - (3u << 20)) / BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX - 1;
+  if (memory_budget <= BWTC_CUDA_SCRATCH_FIXED_BYTES + 64) return 0;
+  uint64 b = (memory_budget - BWTC_CUDA_SCRATCH_FIXED_BYTES) / BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX - 1;
   return b > BWTC_CUDA_MAX_BLOCK ? BWTC_CUDA_MAX_BLOCK : b;
 }
 

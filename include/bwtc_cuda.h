@@ -45,6 +45,7 @@ extern "C" {
 /* Device scratch per suffix (input, text, output, rank, two key + two id buffers, staged ranks, payload bytes, status
  * words) — an upper bound for blocks of 1 MiB and more; bwtc_cuda_scratch_bytes(n) is the exact figure a context for n-byte blocks allocates. */
 #define BWTC_CUDA_SCRATCH_BYTES_PER_SUFFIX 40
+#define BWTC_CUDA_SCRATCH_FIXED_BYTES (8u << 20)  /* + tables that do not grow with the block (status pad rows, sample and prefix tables) */
 
 typedef struct bwtc_cuda_ctx bwtc_cuda_ctx;           /* one stream + device scratch for one in-flight block */
 typedef struct bwtc_cuda_pipeline bwtc_cuda_pipeline; /* several contexts + host workers on one GPU */

@@ -186,5 +186,5 @@ def test_scratch_bytes_is_what_a_context_allocates():
         ctx.close()
         used = free0 - free1
         want = int(lib.bwtc_cuda_scratch_bytes(n))
-        assert want <= bw.SCRATCH_BYTES_PER_SUFFIX * (n + 1) + (3 << 20)
+        assert want <= bw.SCRATCH_BYTES_PER_SUFFIX * (n + 1) + bw.SCRATCH_FIXED_BYTES
         assert abs(used - want) <= (64 << 20), (n, used, want)  # allocator granularity (2 MiB pages per allocation)

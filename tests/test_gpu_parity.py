@@ -110,6 +110,35 @@ def test_any_round0_key_shape_gives_identical_bytes(ctx, oracle, force):
     assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
 
 
+@pytest.mark.parametrize("force", [(0, 0), (1, 4), (3, 4), (2, 8), (5, 8), (64, 8)])
+@pytest.mark.parametrize("kind", ["markov", "dna", "zeros"])
+def test_lazy_ranks_with_any_key_shape(oracle, monkeypatch, force, kind):
+    """Lazy ranks forced (BWTC_LAZY=2) under every round-0 key shape: short keys leave nearly every suffix in a group
+    (more than the lazy list pool holds -> fallback, ranks materialised), long keys leave few (looked up in the sorted
+    keys); text ending in / consisting of zeros exercises the 'short suffix' rule.  Always the oracle's bytes."""
+    monkeypatch.setenv("BWTC_LAZY", "2")
+    if kind == "zeros":
+        x = np.zeros(100003, np.uint8)
+        x[::977] = 1
+    else:
+        x = bw.generate(kind, 300007, seed=23)
+        x[-40:] = x[0]
+    want = oracle.block(x, 8)
+    c = bw.CudaContext(x.size + 1)
+    c.set_round0(*force)
+    try:
+        got = _gpu_block(c, x, 8)
+        raw = np.concatenate([x[::-1], np.zeros(1, np.uint8)])  # the raw contract goes through the same machinery
+        LFr = np.zeros(8, np.uint32)
+        frr = np.zeros(256, np.uint32)
+        rc, wbuf, wLF, wfr = oracle.raw(raw, 8)
+        U = raw.copy()
+        assert c.divbwtf(U, U, LFr, frr) == rc and (U == wbuf).all() and (LFr == wLF).all()
+    finally:
+        c.close()
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all() and (got[2] == want[2]).all()
+
+
 def test_raw_contract_vs_oracle(ctx, oracle):
     """doTransform(byte* begin, uint32 length, vector<uint32>& LF, freqs) on a caller-prepared buffer, as
     test/InverseBwtTest.cpp:57-66 calls it; arbitrary last byte allowed (same semantics as divbwtf)."""
@@ -249,6 +278,13 @@ ENGINE_KNOBS = [
     {"BWTC_DEBUG_FAKE_WATCHDOG": "1"},                               # watchdog fallback: retry with tickets
     {"BWTC_SEG": "0"},                                               # global radix rounds only (no segmented rounds)
     {"BWTC_SEG": "0", "BWTC_RERANK_WINDOW_MB": "1"},                 # bucketed scatter in doubling rounds too
+    {"BWTC_LAZY": "0"},                                              # every rank written in round 0 (no lazy ranks)
+    {"BWTC_LAZY": "2"},                                              # lazy ranks forced: singletons' ranks looked up in the sorted keys;
+                                                                     # the repetitive case falls back (large groups), bit-exact either way
+    {"BWTC_LAZY": "2", "BWTC_STATIC_TILES": "0"},
+    {"BWTC_LAZY": "2", "BWTC_PACK_PRED": "0", "BWTC_AUX_MIN_MIB": "0"},
+    {"BWTC_LAZY": "2", "BWTC_RERANK_WINDOW_MB": "1"},                # the fallback materialises ranks through the bucketed scatter
+    {"BWTC_LAZY": "2", "BWTC_LADDER_FIRST": "0"},
 ]
 
 
@@ -274,6 +310,8 @@ def test_every_engine_path_is_bit_exact(oracle, monkeypatch, knobs):
             assert (got[1] == want[1]).all(), (kind, knobs)
             assert (got[2] == want[2]).all(), (kind, knobs)
         flags = ctx.stats()["flags"]
+        if knobs.get("BWTC_LAZY") == "2":
+            assert flags & 16, "lazy ranks should have been used for the last block"
         if knobs.get("BWTC_STATIC_TILES") == "0" or knobs.get("BWTC_DEBUG_FAKE_WATCHDOG") == "1":
             assert flags & 1, "the look-back kernels should have run with ticket counters"
         else:
