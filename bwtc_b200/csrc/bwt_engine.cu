@@ -118,6 +118,7 @@ struct bwtc_cuda_ctx {
   int lb_watchdog = 0;            // the last transform failed on the look-back watchdog
   int debug_fake_watchdog = 0;    // test hook: pretend the watchdog fired while static tile ids are in use
   int debug_reverse_tiles = 0;    // test hook: static tile ids in REVERSE dispatch order (a real violation)
+  int debug_skip_copies = 0;      // timing experiments only (bit 0: no H2D of host blocks, bit 1: no D2H): results are WRONG
   int ladder_first = 2, ladder_more = 4;  // segmented rounds enqueued speculatively behind a sort round / per retry
   int use_lazy = 1;               // lazy ranks after round 0: 0 never, 1 when a sample of the sorted keys says
                                   // few suffixes stay in groups, 2 always (tests)
@@ -539,7 +540,7 @@ int ensure_ring(bwtc_cuda_ctx* ctx) {
 // ring on the copy-in stream (the memcpy of chunk i+1 overlaps the DMA of chunk i); the kernel stream then waits
 // for the last chunk.
 int upload(bwtc_cuda_ctx* ctx, uint8_t* d_dst, const uint8_t* h_src, size_t n) {
-  if (!n) return 0;
+  if (!n || (ctx->debug_skip_copies & 1)) return 0;
   if (is_pinned_host(h_src)) {
     CK(ctx, cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, ctx->stream));
     return 0;
@@ -951,7 +952,7 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
         CK(ctx, cudaMemcpyAsync(bs->out[k], ctx->d_out + (size_t)k * J.bstride, nk,
                                 bs->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
       }
-    } else if (!J.out_dev) {
+    } else if (!J.out_dev && !(ctx->debug_skip_copies & 2)) {
       CK(ctx, cudaMemcpyAsync(J.h_out, ctx->d_out, n, cudaMemcpyDeviceToHost, st));
     }
     return 0;
@@ -1476,6 +1477,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (const char* e = getenv("BWTC_STATIC_TILES")) c->static_tiles = atoi(e);
   if (const char* e = getenv("BWTC_DEBUG_FAKE_WATCHDOG")) c->debug_fake_watchdog = atoi(e);
   if (const char* e = getenv("BWTC_DEBUG_REVERSE_TILES")) c->debug_reverse_tiles = atoi(e);
+  if (const char* e = getenv("BWTC_DEBUG_SKIP_COPIES")) c->debug_skip_copies = atoi(e);
   if (const char* e = getenv("BWTC_SPIN_WAIT")) c->wait_mode = atoi(e) ? 1 : 0;
   if (const char* e = getenv("BWTC_WAIT_MODE")) c->wait_mode = atoi(e);
   if (const char* e = getenv("BWTC_POLL_SPIN_US")) c->poll_spin_us = std::max(0, atoi(e));
