@@ -118,6 +118,9 @@ struct bwtc_cuda_ctx {
   int lb_watchdog = 0;            // the last transform failed on the look-back watchdog
   int debug_fake_watchdog = 0;    // test hook: pretend the watchdog fired while static tile ids are in use
   int debug_reverse_tiles = 0;    // test hook: static tile ids in REVERSE dispatch order (a real violation)
+  int d2h_kernel = 0;             // BWTC_D2H_KERNEL=1: result copies to pinned host buffers by a copying kernel (k_copy_out)
+                                  // instead of the copy engine — measured no better (profiles/r02_experiments.md), kept as a knob
+  int d2h_ctas = 16;
   int debug_skip_copies = 0;      // timing experiments only (bit 0: no H2D of host blocks, bit 1: no D2H): results are WRONG
   int ladder_first = 2, ladder_more = 4;  // segmented rounds enqueued speculatively behind a sort round / per retry
   int use_lazy = 1;               // lazy ranks after round 0: 0 never, 1 when a sample of the sorted keys says
@@ -524,6 +527,18 @@ bool is_pinned_host(const void* p) {
     return false;
   }
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// Device-side alias of a pinned host buffer (unified addressing), or nullptr if it is not mapped into the device's
+// address space — then the copy engine is used.
+uint8_t* mapped_alias(void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (a.type != cudaMemoryTypeHost) return nullptr;
+  return static_cast<uint8_t*>(a.devicePointer);
 }
 
 int ensure_ring(bwtc_cuda_ctx* ctx) {
@@ -953,7 +968,14 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
                                 bs->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
       }
     } else if (!J.out_dev && !(ctx->debug_skip_copies & 2)) {
-      CK(ctx, cudaMemcpyAsync(J.h_out, ctx->d_out, n, cudaMemcpyDeviceToHost, st));
+      uint8_t* alias = ctx->d2h_kernel ? mapped_alias(J.h_out) : nullptr;
+      if (alias) {
+        k_copy_out<<<ctx->d2h_ctas, 256, 0, st>>>(ctx->d_out, alias, n, ctx->d_state, ctx->d_ctrl());
+        CK(ctx, cudaGetLastError());
+        S.kernel_launches++;
+      } else {
+        CK(ctx, cudaMemcpyAsync(J.h_out, ctx->d_out, n, cudaMemcpyDeviceToHost, st));
+      }
     }
     return 0;
   };
@@ -1478,6 +1500,8 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (const char* e = getenv("BWTC_DEBUG_FAKE_WATCHDOG")) c->debug_fake_watchdog = atoi(e);
   if (const char* e = getenv("BWTC_DEBUG_REVERSE_TILES")) c->debug_reverse_tiles = atoi(e);
   if (const char* e = getenv("BWTC_DEBUG_SKIP_COPIES")) c->debug_skip_copies = atoi(e);
+  if (const char* e = getenv("BWTC_D2H_KERNEL")) c->d2h_kernel = atoi(e);
+  if (const char* e = getenv("BWTC_D2H_CTAS")) c->d2h_ctas = std::max(1, atoi(e));
   if (const char* e = getenv("BWTC_SPIN_WAIT")) c->wait_mode = atoi(e) ? 1 : 0;
   if (const char* e = getenv("BWTC_WAIT_MODE")) c->wait_mode = atoi(e);
   if (const char* e = getenv("BWTC_POLL_SPIN_US")) c->poll_spin_us = std::max(0, atoi(e));

@@ -2028,6 +2028,40 @@ __global__ void __launch_bounds__(1024) k_small_rounds(LadderState* st, PoolPtrs
 
 
 // =====================================================================================================
+// k_copy_out — OPTIONAL (BWTC_D2H_KERNEL=1): the result copy to a PINNED host buffer done by SMs (plain stores through the
+// unified address space) instead of the copy engine.  Background: device-to-host traffic at the rate the end-to-end path
+// needs slows the kernels of all other streams by 12% (tests/gpu_dma_interference.py: 12.6 -> 11.0 GB/s device-resident;
+// host-to-device copies: -1%).  This kernel was built to see whether the copy ENGINE is to blame: it is not — the same
+// bytes written by 16 CTAs cost the same (e2e 10.76 vs 10.70 GB/s), more CTAs cost more.  Not the default.
+// 16-byte accesses where both pointers allow it, bytes at the ragged ends.  Skips an unfinished block (st->m != 0).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_copy_out(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n,
+                                                  const LadderState* __restrict__ st, const uint32_t* __restrict__ ctrl) {
+  if (st->m != 0u || ctrl[CTR_ERR]) return;
+  const uintptr_t mis = (16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;  // bytes until dst is 16-byte aligned
+  const uint32_t head = mis < n ? (uint32_t)mis : n;
+  const uint32_t tidg = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  if (tidg < head) dst[tidg] = src[tidg];
+  const uint32_t body = (n - head) / 16u;
+  uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+  if (((reinterpret_cast<uintptr_t>(src) + head) & 15u) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    for (uint32_t i = tidg; i < body; i += nthr) d4[i] = s4[i];
+  } else {
+    for (uint32_t i = tidg; i < body; i += nthr) {
+      const uint8_t* sp = src + head + (size_t)i * 16u;
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        w[k] = (uint32_t)sp[4 * k] | ((uint32_t)sp[4 * k + 1] << 8) | ((uint32_t)sp[4 * k + 2] << 16) | ((uint32_t)sp[4 * k + 3] << 24);
+      d4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  const uint32_t done = head + body * 16u;
+  if (tidg < n - done) dst[done + tidg] = src[done + tidg];
+}
+
+// =====================================================================================================
 // k_finish — primary index + LFpowers + hole fill (the BWT bytes themselves are emitted by k_rerank as soon
 // as a suffix becomes unique; see EmitParams).  rank[] is now the inverse suffix array.
 //   block contract (BWTransform.cpp:52-64): out[0..n) = L[0..n) with out[pidx] = L[N-1] (hole fill);
