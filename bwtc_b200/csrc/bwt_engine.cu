@@ -33,7 +33,10 @@ constexpr uint32_t RS_TILE64 = RS_BLOCK * RS_IPT64;
 constexpr uint32_t RS_TILE32 = RS_BLOCK * RS_IPT32;
 constexpr uint32_t AUX_TILE = 2048;  // k_pack_round0 / k_build_keys / k_rerank tile
 constexpr int MAX_PASSES = 8;
-constexpr uint32_t HIST_WORDS = MAX_PASSES * 256;
+constexpr uint32_t HIST_WORDS = MAX_PASSES * 512;  // digit histograms of one sort: pass p at p << rb (rb = 8 or 9 bits)
+// Words per look-back status row: 256 (8-bit digits), 512 when the 9-bit digit passes are enabled (BWTC_RADIX9=1).
+inline uint32_t status_row_words_for(int use_radix9) { return use_radix9 ? 512u : 256u; }
+inline int env_radix9() { const char* e = getenv("BWTC_RADIX9"); return e ? atoi(e) : 0; }
 constexpr uint32_t TEXT_PAD = 64;
 
 thread_local char g_err[512] = "";
@@ -89,7 +92,7 @@ struct bwtc_cuda_ctx {
   uint8_t* d_aux[2] = {nullptr, nullptr};    // ping-pong one-byte payload of the round-0 sort (predecessor codes), N each
   uint32_t* d_scat = nullptr;     // u32[N]: staged ranks of the bucketed scatter (the ids go to the idle id buffer)
   uint32_t* d_zero = nullptr;     // [ctrl CTR_WORDS][hist HIST_WORDS][tstate rows of max_aux_tiles] zeroed per round
-  uint32_t* d_status = nullptr;   // [MAX_PASSES][LB_PAD_ROWS + max_rs_tiles][256] radix look-back words; the pad rows in
+  uint32_t* d_status = nullptr;   // [MAX_PASSES][LB_PAD_ROWS + max_rs_tiles][status_row_words] radix look-back words; the pad rows in
                                   // front of every pass hold "prefix 0" for ever, so a walk needs no bounds check
   uint32_t* d_tilecnt = nullptr;  // [2][max_aux_tiles]: per-tile live counts of k_rerank and their exclusive prefix,
                                   // then [max_aux_tiles][MAX_RERANK_WINDOWS+1] bucket offsets of the bucketed scatter
@@ -123,6 +126,10 @@ struct bwtc_cuda_ctx {
   int d2h_ctas = 16;
   int debug_skip_copies = 0;      // timing experiments only (bit 0: no H2D of host blocks, bit 1: no D2H): results are WRONG
   int ladder_first = 2, ladder_more = 4;  // segmented rounds enqueued speculatively behind a sort round / per retry
+  int use_radix9 = 0;             // BWTC_RADIX9=1: 9-bit digits for 64-bit-key sorts whenever that saves a pass.  Measured
+                                  // slower (a 9-bit pass costs +23%, 7 of them more than 8 eight-bit ones): kept as an
+                                  // experiment, profiles/r02_experiments.md
+  uint32_t status_row_words = 256;
   int use_lazy = 1;               // lazy ranks after round 0: 0 never, 1 when a sample of the sorted keys says
                                   // few suffixes stay in groups, 2 always (tests)
   uint32_t lazy_min_suffixes = 4u << 20;
@@ -159,10 +166,10 @@ struct bwtc_cuda_ctx {
 
 namespace {
 
-template <typename KeyT, int IPT, bool IOTA, bool AUX>
+template <typename KeyT, int IPT, bool IOTA, bool AUX, int RB = 8>
 int set_pass_attr(bwtc_cuda_ctx* ctx) {
-  CK(ctx, cudaFuncSetAttribute(k_radix_pass<KeyT, RS_BLOCK, IPT, IOTA, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)RadixPassSmem<KeyT, RS_BLOCK, IPT, AUX>::bytes));
+  CK(ctx, cudaFuncSetAttribute(k_radix_pass<KeyT, RS_BLOCK, IPT, IOTA, AUX, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)RadixPassSmem<KeyT, RS_BLOCK, IPT, AUX, RB>::bytes));
   return 0;
 }
 
@@ -195,6 +202,7 @@ void ctx_free(bwtc_cuda_ctx* c) {
 
 struct Round0Plan {
   uint32_t sigma, bits, chars, keybytes, npass;
+  uint32_t rb;        // digit width of the round-0 sort: 9 when that saves a pass over 8-bit digits (64-bit keys only)
   PackParams pp;
   bool has_memory;    // the 8-gram sample says the source is not i.i.d.-like (text, repeats)
   double live_pred;   // i.i.d.-like sources: predicted fraction of suffixes still tied after round 0, L(chars)
@@ -277,6 +285,11 @@ void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* pr
   pl->chars = chars;
   pl->keybytes = keybytes;
   pl->npass = div_up((uint64_t)chars * b + blk_bits, 8);
+  pl->rb = 8;
+  if (ctx->use_radix9 && keybytes == 8 && div_up((uint64_t)chars * b + blk_bits, 9) < pl->npass) {
+    pl->rb = 9;
+    pl->npass = div_up((uint64_t)chars * b + blk_bits, 9);
+  }
   pl->pp.bits = b;
   pl->pp.chars = chars;
   pl->pp.nblocks = 1;
@@ -307,6 +320,12 @@ inline uint32_t tile_slot(const bwtc_cuda_ctx* ctx, uint32_t ticket_word) {
   return ctx->debug_reverse_tiles ? CTR_STATIC_REV : CTR_STATIC;
 }
 
+// Row 0 of the look-back status words of digit pass p (LB_PAD_ROWS rows of "prefix 0" words sit in front of it, for
+// either row width).
+inline uint32_t* status_rows(const bwtc_cuda_ctx* ctx, int p) {
+  return ctx->d_status + ((size_t)p * (ctx->max_rs_tiles + LB_PAD_ROWS) + LB_PAD_ROWS) * ctx->status_row_words;
+}
+
 struct PassTimer {
   bwtc_cuda_ctx* ctx;
   size_t used = 0;
@@ -327,12 +346,12 @@ struct PassTimer {
 
 // One LSD radix sort of m records: executes the digit passes whose bit is set in pass_mask, ping-ponging
 // between buffer 0 and 1.  Records start in buffer `cur` (0); returns the buffer holding the result.
-template <typename KeyT, int IPT, bool AUX>
+template <typename KeyT, int IPT, bool AUX, int RB = 8>
 int run_sort_impl(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota, uint32_t iota_top, int* cur_io,
                   PassTimer* pt, uint32_t* passes_done, uint32_t pack_bits, uint32_t topshift, uint32_t pred_mask) {
   constexpr uint32_t TILE = RS_BLOCK * IPT;
   const uint32_t tiles = div_up(m, TILE);
-  const size_t smem = RadixPassSmem<KeyT, RS_BLOCK, IPT, AUX>::bytes;
+  const size_t smem = RadixPassSmem<KeyT, RS_BLOCK, IPT, AUX, RB>::bytes;
   int cur = *cur_io;
   bool iota = first_iota;
   uint32_t done = 0;
@@ -340,17 +359,17 @@ int run_sort_impl(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first
     if (!((pass_mask >> p) & 1u)) continue;
     const KeyT* kin = static_cast<const KeyT*>(ctx->d_keys[cur]);
     KeyT* kout = static_cast<KeyT*>(ctx->d_keys[cur ^ 1]);
-    uint32_t* status = ctx->d_status + ((size_t)p * (ctx->max_rs_tiles + LB_PAD_ROWS) + LB_PAD_ROWS) * 256u;
+    uint32_t* status = status_rows(ctx, p);
     if (pt->begin()) return BWTC_CUDA_ECUDA;
     if (iota)
-      k_radix_pass<KeyT, RS_BLOCK, IPT, true, AUX><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
-          kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
+      k_radix_pass<KeyT, RS_BLOCK, IPT, true, AUX, RB><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
+          kin, nullptr, kout, ctx->d_idx[cur ^ 1], m, (uint32_t)RB * p, ctx->d_hist() + ((size_t)p << RB), status, ctx->d_ctrl(),
           tile_slot(ctx, (uint32_t)(CTR_PASS0 + p)), iota_top, pack_bits, topshift, pred_mask, nullptr,
           ctx->d_aux[cur ^ 1]);
     else
-      k_radix_pass<KeyT, RS_BLOCK, IPT, false, AUX><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
-          kin, ctx->d_idx[cur], kout, ctx->d_idx[cur ^ 1], m, 8u * p, ctx->d_hist() + p * 256, status, ctx->d_ctrl(),
-          tile_slot(ctx, (uint32_t)(CTR_PASS0 + p)), iota_top, 0u, 0u, 0u, ctx->d_aux[cur], ctx->d_aux[cur ^ 1]);
+      k_radix_pass<KeyT, RS_BLOCK, IPT, false, AUX, RB><<<tiles, RS_BLOCK, smem, ctx->stream>>>(
+          kin, ctx->d_idx[cur], kout, ctx->d_idx[cur ^ 1], m, (uint32_t)RB * p, ctx->d_hist() + ((size_t)p << RB), status,
+          ctx->d_ctrl(), tile_slot(ctx, (uint32_t)(CTR_PASS0 + p)), iota_top, 0u, 0u, 0u, ctx->d_aux[cur], ctx->d_aux[cur ^ 1]);
     CK(ctx, cudaGetLastError());
     if (pt->end()) return BWTC_CUDA_ECUDA;
     ctx->stats.kernel_launches++;
@@ -370,10 +389,21 @@ int run_sort_impl(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first
 // One LSD radix sort of m records: executes the digit passes whose bit is set in pass_mask, ping-ponging
 // between buffer 0 and 1.  Records start in buffer `cur` (0); returns the buffer holding the result.
 // aux: a one-byte payload (predecessor character code) is produced by the first pass and carried along.
+// rb: digit width, 8 or 9 bits (9 only for 64-bit keys); pass p sorts on bits [rb*p, rb*p + rb).
 template <typename KeyT, int IPT>
 int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota, uint32_t iota_top, int* cur_io,
              PassTimer* pt, uint32_t* passes_done, uint32_t pack_bits = 0, uint32_t topshift = 0,
-             uint32_t pred_mask = 0xFFFFFFFFu, bool aux = false) {
+             uint32_t pred_mask = 0xFFFFFFFFu, bool aux = false, uint32_t rb = 8) {
+  if constexpr (sizeof(KeyT) == 8) {
+    if (rb == 9) {
+      if (aux)
+        return run_sort_impl<KeyT, IPT, true, 9>(ctx, m, pass_mask, first_iota, iota_top, cur_io, pt, passes_done, pack_bits,
+                                                 topshift, pred_mask);
+      return run_sort_impl<KeyT, IPT, false, 9>(ctx, m, pass_mask, first_iota, iota_top, cur_io, pt, passes_done, pack_bits,
+                                                topshift, pred_mask);
+    }
+  }
+  if (rb != 8) { set_err(ctx->err, "run_sort: %u-bit digits are not built for this key type", rb); return BWTC_CUDA_EINTERNAL; }
   if (aux)
     return run_sort_impl<KeyT, IPT, true>(ctx, m, pass_mask, first_iota, iota_top, cur_io, pt, passes_done, pack_bits, topshift,
                                           pred_mask);
@@ -381,7 +411,7 @@ int run_sort(bwtc_cuda_ctx* ctx, uint32_t m, uint32_t pass_mask, bool first_iota
                                          pred_mask);
 }
 
-int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m, uint32_t rs_tile, uint32_t pass_mask) {
+int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m, uint32_t rs_tile, uint32_t pass_mask, uint32_t rb = 8) {
   const uint32_t aux_tiles = div_up(m, AUX_TILE);
   CK(ctx, cudaMemsetAsync(ctx->d_zero + CTR_STICKY, 0,
                           (size_t)(CTR_WORDS - CTR_STICKY + HIST_WORDS) * 4 + (size_t)rerank_launches(ctx, N, m) * ctx->max_aux_tiles * 8,
@@ -389,8 +419,7 @@ int zero_round_state(bwtc_cuda_ctx* ctx, uint32_t N, uint32_t m, uint32_t rs_til
   const uint32_t tiles = div_up(m, rs_tile);
   for (int p = 0; p < MAX_PASSES; ++p)
     if ((pass_mask >> p) & 1u)
-      CK(ctx, cudaMemsetAsync(ctx->d_status + ((size_t)p * (ctx->max_rs_tiles + LB_PAD_ROWS) + LB_PAD_ROWS) * 256u, 0,
-                              (size_t)tiles * 1024u, ctx->stream));
+      CK(ctx, cudaMemsetAsync(status_rows(ctx, p), 0, ((size_t)tiles * 4u) << rb, ctx->stream));
   return 0;
 }
 
@@ -780,7 +809,7 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
   // ---- round 0: pack keys (+ all digit histograms), sort, re-rank
   const uint32_t rs_tile0 = pl.keybytes == 4 ? RS_TILE32 : RS_TILE64;
   const uint32_t all0 = (1u << pl.npass) - 1u;
-  if (zero_round_state(ctx, N, N, rs_tile0, all0)) return BWTC_CUDA_ECUDA;
+  if (zero_round_state(ctx, N, N, rs_tile0, all0, pl.rb)) return BWTC_CUDA_ECUDA;
   {
     const uint32_t ptiles = div_up(N, AUX_TILE);
     const int grid = (int)(ptiles < (uint32_t)(ctx->sm_count * 4) ? ptiles : (uint32_t)(ctx->sm_count * 4));
@@ -791,27 +820,28 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
     const uint32_t keybits = pl.chars * pl.bits;
     for (uint32_t p = 0; p < pl.npass; ++p) {
       int rep = -1;
-      const bool full_p = (8 * p + 8 <= keybits);
+      const uint32_t rb = pl.rb;
+      const bool full_p = (rb * p + rb <= keybits);
       if (full_p && N > 64 && !bs)  // (a batch counts every digit directly: block numbers sit above the characters)
         for (uint32_t r = 0; r < p; ++r)
-          if (((hist_mask >> r) & 1u) && (8 * r) % pl.bits == (8 * p) % pl.bits && (8 * (p - r)) % pl.bits == 0) { rep = (int)r; break; }
+          if (((hist_mask >> r) & 1u) && (rb * r) % pl.bits == (rb * p) % pl.bits && (rb * (p - r)) % pl.bits == 0) { rep = (int)r; break; }
       if (rep < 0) {
         hist_mask |= 1u << p;
       } else {
         dp.p[dp.count] = (uint8_t)p;
         dp.r[dp.count] = (uint8_t)rep;
-        dp.t[dp.count] = (uint8_t)(8 * (p - (uint32_t)rep) / pl.bits);
+        dp.t[dp.count] = (uint8_t)(pl.rb * (p - (uint32_t)rep) / pl.bits);
         dp.count++;
       }
     }
     if (pl.keybytes == 4) {
       k_pack_round0<uint32_t><<<grid, 256, 0, st>>>(d_text, N, static_cast<uint32_t*>(ctx->d_keys[0]), pl.pp,
-                                                     ctx->d_hist(), hist_mask, ptiles);
-      if (dp.count) k_hist_derive<uint32_t><<<dp.count, 256, 0, st>>>(d_text, N, pl.pp, dp, ctx->d_hist());
+                                                     ctx->d_hist(), hist_mask, ptiles, pl.rb);
+      if (dp.count) k_hist_derive<uint32_t><<<dp.count, 256, 0, st>>>(d_text, N, pl.pp, dp, ctx->d_hist(), pl.rb);
     } else {
       k_pack_round0<unsigned long long><<<grid, 256, 0, st>>>(d_text, N, static_cast<unsigned long long*>(ctx->d_keys[0]),
-                                                               pl.pp, ctx->d_hist(), hist_mask, ptiles);
-      if (dp.count) k_hist_derive<unsigned long long><<<dp.count, 256, 0, st>>>(d_text, N, pl.pp, dp, ctx->d_hist());
+                                                               pl.pp, ctx->d_hist(), hist_mask, ptiles, pl.rb);
+      if (dp.count) k_hist_derive<unsigned long long><<<dp.count, 256, 0, st>>>(d_text, N, pl.pp, dp, ctx->d_hist(), pl.rb);
     }
     if (dp.count) S.kernel_launches++;
     CK(ctx, cudaGetLastError());
@@ -839,7 +869,7 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
                                       pred_mask, aux_pred);
   else
     rc = run_sort<unsigned long long, RS_IPT64>(ctx, N, mask0, true, N - 1, &cur, &pt, &pdone, pack_pred ? id_bits : 0u,
-                                                topshift, pred_mask, aux_pred);
+                                                topshift, pred_mask, aux_pred, pl.rb);
   if (rc) return rc;
   const size_t round0_events = pt.used;
   S.sort0_launches = S.sort_launches;
@@ -983,7 +1013,11 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
   const int lo_bits = (int)ceil_log2_u64((uint64_t)N + 1);  // rank[i+h] + 1 in [0, N]
   // high part = (rank of the group head) >> 1 (k_build_keys): heads of live groups are <= N - 2
   const int hi_bits = N > 3 ? (int)ceil_log2_u64((((uint64_t)N - 2) >> 1) + 1) : 1;
-  const uint32_t npassd = div_up((uint64_t)(lo_bits + hi_bits), 8);
+  uint32_t npassd = div_up((uint64_t)(lo_bits + hi_bits), 8), rbd = 8;
+  if (ctx->use_radix9 && div_up((uint64_t)(lo_bits + hi_bits), 9) < npassd) {  // 9-bit digits when they save a pass
+    npassd = div_up((uint64_t)(lo_bits + hi_bits), 9);
+    rbd = 9;
+  }
   const uint32_t maskd = (1u << npassd) - 1u;
   bool lists_pending = true, first_chunk = true, out_enqueued = false, finished = false;
   // lean chunk: behind a global radix round whose groups were still far above the segmented-round limit nothing sort-free
@@ -1030,7 +1064,7 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
       // run statistics of the (finished) output: symbols -> d_aux[0], start positions -> d_scat, both idle by now; tile
       // counts in the look-back status area (cleared again before any later digit pass uses it)
       const uint32_t rtiles = div_up(n, RUN_TILE);
-      uint32_t* rcnt = ctx->d_status + (size_t)LB_PAD_ROWS * 256u;
+      uint32_t* rcnt = status_rows(ctx, 0);
       uint32_t* rexcl = rcnt + rtiles;
       const uint32_t cap_dev = std::min<uint32_t>(J.runs->capacity, n);
       k_run_count<<<rtiles, 256, 0, st>>>(J.d_dst, n, rcnt, ctx->d_state);
@@ -1140,7 +1174,7 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
       set_err(ctx->err, "internal: global sort requested after a segmented round (maxgroup %u)", H.maxgroup);
       return BWTC_CUDA_EINTERNAL;
     }
-    if (zero_round_state(ctx, N, m, RS_TILE64, maskd)) return BWTC_CUDA_ECUDA;
+    if (zero_round_state(ctx, N, m, RS_TILE64, maskd, rbd)) return BWTC_CUDA_ECUDA;
     uint32_t expect_cursor = 0xFFFFFFFFu;
     if (from_list) {
       if (!have_lists) {
@@ -1153,7 +1187,7 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
       const int grid = (int)(bt < (uint32_t)(ctx->sm_count * 8) ? bt : (uint32_t)(ctx->sm_count * 8));
       k_build_from_list<<<grid, 256, 0, st>>>(pool.p[2 * cur + 1], m, ctx->d_rank, N, h32, lo_bits,
                                               static_cast<unsigned long long*>(ctx->d_keys[tb]), ctx->d_idx[tb],
-                                              ctx->d_hist(), (int)npassd, ctx->d_ctrl());
+                                              ctx->d_hist(), (int)npassd, ctx->d_ctrl(), rbd);
       CK(ctx, cudaGetLastError());
       S.kernel_launches++;
       S.algorithmic_bytes += (uint64_t)m * (4 + 8 + 12);
@@ -1162,14 +1196,14 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
       const uint32_t btiles = div_up(N, AUX_TILE);
       const int grid = (int)(btiles < (uint32_t)(ctx->sm_count * 8) ? btiles : (uint32_t)(ctx->sm_count * 8));
       k_build_keys<<<grid, 256, 0, st>>>(ctx->d_rank, N, h32, lo_bits, static_cast<unsigned long long*>(ctx->d_keys[0]),
-                                         ctx->d_idx[0], ctx->d_ctrl(), ctx->d_hist(), (int)npassd, btiles);
+                                         ctx->d_idx[0], ctx->d_ctrl(), ctx->d_hist(), (int)npassd, btiles, rbd);
       CK(ctx, cudaGetLastError());
       S.kernel_launches++;
       S.algorithmic_bytes += (uint64_t)N * 4 + (uint64_t)m * 12;
       cur = 0;
       expect_cursor = m;
     }
-    rc = run_sort<unsigned long long, RS_IPT64>(ctx, m, maskd, false, 0, &cur, &pt, &pdone);
+    rc = run_sort<unsigned long long, RS_IPT64>(ctx, m, maskd, false, 0, &cur, &pt, &pdone, 0, 0, 0xFFFFFFFFu, false, rbd);
     if (rc) return rc;
     {
       RerankParams rp;
@@ -1509,6 +1543,8 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (const char* e = getenv("BWTC_LADDER_FIRST")) c->ladder_first = std::max(0, atoi(e));
   if (const char* e = getenv("BWTC_LADDER_MORE")) c->ladder_more = std::max(1, atoi(e));
   if (const char* e = getenv("BWTC_LAZY")) c->use_lazy = atoi(e);
+  c->use_radix9 = env_radix9();
+  c->status_row_words = status_row_words_for(c->use_radix9);
   if (const char* e = getenv("BWTC_LAZY_MIN_MIB")) c->lazy_min_suffixes = (uint32_t)std::max(0L, atol(e)) << 20;
   if (const char* e = getenv("BWTC_LAZY_MAX_LIVE")) c->lazy_max_live = atof(e);
   if (const char* e = getenv("BWTC_SEG")) c->use_seg = atoi(e);
@@ -1558,7 +1594,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_idx[0], N * 4);
   ALLOC(c->d_idx[1], N * 4);
   ALLOC(c->d_zero, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)MAX_RERANK_WINDOWS * c->max_aux_tiles * 8 + 64);
-  ALLOC(c->d_status, (size_t)MAX_PASSES * (c->max_rs_tiles + LB_PAD_ROWS) * 1024u);
+  ALLOC(c->d_status, (size_t)MAX_PASSES * (c->max_rs_tiles + LB_PAD_ROWS) * c->status_row_words * 4u);
   ALLOC(c->d_LF, (size_t)LF_WORDS * 4);
   ALLOC(c->d_state, sizeof(LadderState));
   ALLOC(c->d_livebits, (N / 32 + 4) * 4);
@@ -1573,10 +1609,9 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_aux[1], padded);
 #undef ALLOC
   if (!rc) {  // pad rows of the look-back status: "inclusive prefix = 0", never overwritten
-    std::vector<uint32_t> pad((size_t)LB_PAD_ROWS * 256, LB_PAD_WORD);
+    std::vector<uint32_t> pad((size_t)LB_PAD_ROWS * c->status_row_words, LB_PAD_WORD);
     for (int p = 0; p < MAX_PASSES && !rc; ++p) {
-      e = cudaMemcpy(c->d_status + (size_t)p * (c->max_rs_tiles + LB_PAD_ROWS) * 256u, pad.data(), pad.size() * 4,
-                     cudaMemcpyHostToDevice);
+      e = cudaMemcpy(status_rows(c, p) - pad.size(), pad.data(), pad.size() * 4, cudaMemcpyHostToDevice);
       if (e != cudaSuccess) { set_err(g_err, "cudaMemcpy(status pad): %s", cudaGetErrorString(e)); rc = BWTC_CUDA_ECUDA; }
     }
   }
@@ -1610,6 +1645,10 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
     r2 |= set_pass_attr<uint32_t, RS_IPT32, false, true>(c);
     r2 |= set_pass_attr<unsigned long long, RS_IPT64, true, true>(c);
     r2 |= set_pass_attr<unsigned long long, RS_IPT64, false, true>(c);
+    r2 |= set_pass_attr<unsigned long long, RS_IPT64, true, false, 9>(c);
+    r2 |= set_pass_attr<unsigned long long, RS_IPT64, false, false, 9>(c);
+    r2 |= set_pass_attr<unsigned long long, RS_IPT64, true, true, 9>(c);
+    r2 |= set_pass_attr<unsigned long long, RS_IPT64, false, true, 9>(c);
     if (r2) { set_err(g_err, "%s", c->err); rc = BWTC_CUDA_ECUDA; }
   }
   if (rc) { ctx_free(c); return rc; }
@@ -1638,7 +1677,7 @@ uint64_t bwtc_cuda_scratch_bytes(uint32_t max_block_bytes) {
   b += 2 * N * 8 + 2 * N * 4;                               // d_keys[2], d_idx[2]
   b += N * 4 + 64;                                          // d_scat
   b += (uint64_t)(CTR_WORDS + HIST_WORDS) * 4 + (uint64_t)MAX_RERANK_WINDOWS * aux_tiles * 8 + 64;  // d_zero
-  b += (uint64_t)MAX_PASSES * (rs_tiles + LB_PAD_ROWS) * 1024u;                                       // d_status
+  b += (uint64_t)MAX_PASSES * (rs_tiles + LB_PAD_ROWS) * status_row_words_for(env_radix9()) * 4u;     // d_status
   b += (uint64_t)LF_WORDS * 4 + sizeof(LadderState) + (uint64_t)MAX_BATCH * 256 * 4 + (uint64_t)MAX_BATCH * sizeof(void*);
   b += (uint64_t)WS_SLOTS * 12 + 64;                        // d_wtab
   b += aux_tiles * (2 + MAX_RERANK_WINDOWS + 1) * 4 + 64;   // d_tilecnt

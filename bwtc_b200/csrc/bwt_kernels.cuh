@@ -62,6 +62,11 @@ constexpr int LB_PAD_ROWS = 8;  // rows of "prefix 0" in front of tile 0 (>= LB_
 // and a round trip of RT cycles the look-back settles at L = RT / (1 - RT / (dt * BATCH)): the batch must
 // satisfy dt * BATCH >> RT or the walk chases an ever longer chain of aggregate-only predecessors.
 constexpr int LB_BATCH = BWTC_LB_BATCH;
+#ifndef BWTC_LB_BATCH9
+#define BWTC_LB_BATCH9 2
+#endif
+constexpr int LB_BATCH9 = BWTC_LB_BATCH9;  // per digit in the 9-bit pass (two digits per thread); measured 2/4/6/8: 1.894/1.905/1.935/1.990 ms per sort
+static_assert(LB_BATCH9 <= LB_PAD_ROWS, "the look-back batch must not read past the pad rows");
 static_assert(LB_BATCH <= LB_PAD_ROWS, "the look-back batch must not read past the pad rows");
 
 // Record streams of k_radix_pass: plain loads, streaming (evict-first) stores.  Measured on the 32 MiB Markov block:
@@ -146,6 +151,27 @@ __device__ __forceinline__ uint32_t match_digit8(uint32_t d) {
   return m;
 }
 
+// The same with 9 ballots (9-bit digits, BWTC radix-9 passes).
+__device__ __forceinline__ uint32_t match_digit9(uint32_t d) {
+  uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %1, %2;\n"
+        "setp.ne.u32 p, t, 0;\n"
+        "vote.sync.ballot.b32 t, p, 0xffffffff;\n"
+        "@p and.b32 %0, %0, t;\n"
+        "@!p lop3.b32 %0, %0, t, 0, 0x30;\n"
+        "}\n"
+        : "+r"(m)
+        : "r"(d), "r"(1u << b));
+  }
+  return m;
+}
+
 // Exclusive sum-scan over the first 256 threads of the CTA (value of threads >= 256 is ignored).
 // Every thread of the CTA must call it (contains __syncthreads). s_tot: 8 words of shared memory.
 __device__ __forceinline__ uint32_t scan256_excl(uint32_t v, uint32_t* s_tot) {
@@ -166,6 +192,34 @@ __device__ __forceinline__ uint32_t scan256_excl(uint32_t v, uint32_t* s_tot) {
   }
   __syncthreads();
   return base + inc - v;
+}
+
+// Two exclusive sum-scans over the 256 threads of the CTA at once (same barriers); tot0 / tot1 receive the totals.
+// s_tot: 16 words of shared memory.
+__device__ __forceinline__ void scan256_excl2(uint32_t v0, uint32_t v1, uint32_t* s_tot, uint32_t& e0, uint32_t& e1,
+                                              uint32_t& tot0, uint32_t& tot1) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  uint32_t i0 = v0, i1 = v1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t0 = __shfl_up_sync(0xFFFFFFFFu, i0, o);
+    const uint32_t t1 = __shfl_up_sync(0xFFFFFFFFu, i1, o);
+    if (lane >= o) { i0 += t0; i1 += t1; }
+  }
+  if (w < 8 && lane == 31) { s_tot[w] = i0; s_tot[8 + w] = i1; }
+  __syncthreads();
+  uint32_t b0 = 0, b1 = 0, a0 = 0, a1 = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t t0 = s_tot[i], t1 = s_tot[8 + i];
+    a0 += t0; a1 += t1;
+    if (i < w) { b0 += t0; b1 += t1; }
+  }
+  __syncthreads();
+  e0 = b0 + i0 - v0;
+  e1 = b1 + i1 - v1;
+  tot0 = a0;
+  tot1 = a1;
 }
 
 // =====================================================================================================
@@ -326,15 +380,18 @@ struct PackParams {
 template <typename KeyT>
 __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__ text, uint32_t N,
                                                      KeyT* __restrict__ keys, PackParams pp,
-                                                     uint32_t* __restrict__ hist, uint32_t hist_mask, uint32_t ntiles) {
+                                                     uint32_t* __restrict__ hist, uint32_t hist_mask, uint32_t ntiles,
+                                                     uint32_t rb) {
+  // rb: digit width of the sort that follows (8 or 9); digit p = (key >> rb*p) & (2^rb - 1), histogram p at hist + p * 2^rb
   constexpr int BLOCK = 256, IPT = 8, TILE = BLOCK * IPT;
   __shared__ uint8_t s_lut[256];
   __shared__ uint8_t s_code[TILE + 64];
-  __shared__ uint32_t s_hist[8 * 256];
+  __shared__ uint32_t s_hist[8 * 512];
   const int tid = threadIdx.x;
+  const uint32_t dmask = (1u << rb) - 1u;
   s_lut[tid] = pp.lut[tid];
 #pragma unroll
-  for (int p = 0; p < 8; ++p) s_hist[p * 256 + tid] = 0;
+  for (int p = 0; p < 16; ++p) s_hist[p * 256 + tid] = 0;
   __syncthreads();
   const uint32_t c = pp.chars, b = pp.bits;
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -403,7 +460,7 @@ __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__
         if (t + k < N) {
 #pragma unroll
           for (int p = 0; p < (int)(sizeof(KeyT)); ++p)
-            if ((hist_mask >> p) & 1u) atomicAdd(&s_hist[p * 256 + (uint32_t)((out[k] >> (8 * p)) & 0xFF)], 1u);
+            if ((hist_mask >> p) & 1u) atomicAdd(&s_hist[(p << rb) + ((uint32_t)(out[k] >> (rb * p)) & dmask)], 1u);
         }
       }
     }
@@ -412,8 +469,10 @@ __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__
 #pragma unroll
   for (int p = 0; p < (int)(sizeof(KeyT)); ++p) {
     if (!((hist_mask >> p) & 1u)) continue;
-    const uint32_t v = s_hist[p * 256 + tid];
-    if (v) atomicAdd(&hist[p * 256 + tid], v);
+    for (uint32_t e = tid; e <= dmask; e += BLOCK) {
+      const uint32_t v = s_hist[(p << rb) + e];
+      if (v) atomicAdd(&hist[(p << rb) + e], v);
+    }
   }
 }
 
@@ -444,26 +503,27 @@ __device__ __forceinline__ KeyT pack_key_at(const uint8_t* __restrict__ text, ui
 
 template <typename KeyT>
 __global__ void __launch_bounds__(256) k_hist_derive(const uint8_t* __restrict__ text, uint32_t N, PackParams pp,
-                                                     DeriveParams dp, uint32_t* __restrict__ hist) {
+                                                     DeriveParams dp, uint32_t* __restrict__ hist, uint32_t rb) {
   __shared__ uint8_t s_lut[256];
-  __shared__ uint32_t s_h[256];
+  __shared__ uint32_t s_h[512];
   const int tid = threadIdx.x;
   const uint32_t p = dp.p[blockIdx.x], r = dp.r[blockIdx.x], t = dp.t[blockIdx.x];
+  const uint32_t dmask = (1u << rb) - 1u;
   s_lut[tid] = pp.lut[tid];
-  s_h[tid] = hist[r * 256 + tid];
+  for (uint32_t e = tid; e <= dmask; e += 256) s_h[e] = hist[(r << rb) + e];
   __syncthreads();
   if ((uint32_t)tid < t) {
     if ((uint32_t)tid < N) {  // head term: suffix i = tid counted for digit p
       const KeyT kh = pack_key_at<KeyT>(text, N, (uint32_t)tid, s_lut, pp.bits, pp.chars);
-      atomicAdd(&s_h[(uint32_t)((kh >> (8 * p)) & 0xFF)], 1u);
+      atomicAdd(&s_h[(uint32_t)(kh >> (rb * p)) & dmask], 1u);
     }
     if ((uint32_t)tid < N) {  // tail term: suffix i = N-1-tid was counted for digit r but has no partner
       const KeyT kt = pack_key_at<KeyT>(text, N, N - 1u - (uint32_t)tid, s_lut, pp.bits, pp.chars);
-      atomicSub(&s_h[(uint32_t)((kt >> (8 * r)) & 0xFF)], 1u);
+      atomicSub(&s_h[(uint32_t)(kt >> (rb * r)) & dmask], 1u);
     }
   }
   __syncthreads();
-  hist[p * 256 + tid] = s_h[tid];
+  for (uint32_t e = tid; e <= dmask; e += 256) hist[(p << rb) + e] = s_h[e];
 }
 
 // =====================================================================================================
@@ -477,15 +537,17 @@ __global__ void __launch_bounds__(256) k_hist_derive(const uint8_t* __restrict__
 __global__ void __launch_bounds__(256) k_build_keys(const uint32_t* __restrict__ rank, uint32_t N, uint32_t h,
                                                     int lo_bits, unsigned long long* __restrict__ keys,
                                                     uint32_t* __restrict__ idx, uint32_t* __restrict__ ctrl,
-                                                    uint32_t* __restrict__ hist, int npass, uint32_t ntiles) {
+                                                    uint32_t* __restrict__ hist, int npass, uint32_t ntiles,
+                                                    uint32_t rb) {
   constexpr int BLOCK = 256, IPT = 8, TILE = BLOCK * IPT, WARPS = BLOCK / 32;
-  __shared__ uint32_t s_hist[8 * 256];
+  __shared__ uint32_t s_hist[8 * 512];
   __shared__ uint32_t s_wtot[WARPS];
   __shared__ uint32_t s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t dmask = (1u << rb) - 1u;
   if (ctrl[CTR_ERR]) return;
 #pragma unroll
-  for (int p = 0; p < 8; ++p) s_hist[p * 256 + tid] = 0;
+  for (int p = 0; p < 16; ++p) s_hist[p * 256 + tid] = 0;
   __syncthreads();
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // thread-blocked: 8 consecutive suffixes per thread, two 128-bit loads issued back to back (rank[] is
@@ -544,15 +606,16 @@ __global__ void __launch_bounds__(256) k_build_keys(const uint32_t* __restrict__
         keys[pos] = key;
         idx[pos] = (i0 + k) | ((r[k] & 1u) << 31);
         ++pos;
-        for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + (uint32_t)((key >> (8 * p)) & 0xFF)], 1u);
+        for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[(p << rb) + ((uint32_t)(key >> (rb * p)) & dmask)], 1u);
       }
     }
   }
   __syncthreads();
-  for (int p = 0; p < npass; ++p) {
-    const uint32_t v = s_hist[p * 256 + tid];
-    if (v) atomicAdd(&hist[p * 256 + tid], v);
-  }
+  for (int p = 0; p < npass; ++p)
+    for (uint32_t e = tid; e <= dmask; e += BLOCK) {
+      const uint32_t v = s_hist[(p << rb) + e];
+      if (v) atomicAdd(&hist[(p << rb) + e], v);
+    }
 }
 
 // =====================================================================================================
@@ -577,18 +640,25 @@ __device__ unsigned long long* g_prof_buf = nullptr;  // [tiles][16] SM-clock st
 #define BWTC_PROF(k) do { } while (0)
 #endif
 
-template <typename KeyT, int BLOCK, int IPT, bool AUX = false>
+template <typename KeyT, int BLOCK, int IPT, bool AUX = false, int RB = 8>
 struct RadixPassSmem {
   static constexpr int TILE = BLOCK * IPT;
   static constexpr int WARPS = BLOCK / 32;
   static constexpr size_t bytes =
-      (sizeof(KeyT) + 4) * TILE + sizeof(uint32_t) * (WARPS * 256 + 256 + 256 + 32) + (AUX ? TILE : 0);
+      (sizeof(KeyT) + 4) * TILE + sizeof(uint32_t) * (WARPS * 256 + (1 << RB) + 32) + (AUX ? TILE : 0);
 };
 
 // AUX: a third, one-byte payload travels with every record — the dense code of the character preceding the
 // suffix, for blocks whose id has no spare bits for it (pack_bits) and whose text is too large for an L2-resident
 // gather at emission time.  The IOTA pass produces it (top character of the next key), later passes carry it.
-template <typename KeyT, int BLOCK, int IPT, bool IOTA, bool AUX = false>
+// RB = 9 (experiment, BWTC_RADIX9=1; MEASURED SLOWER: one 9-bit pass over the 32 MiB block's records takes 0.272 ms against
+// 0.220 ms, so 7 of them lose to 8 eight-bit passes — profiles/r02_experiments.md): nine-bit digits (512 bins; a
+// 55..63-bit key then takes 7 passes instead of 8).  The CTA keeps its shape: every
+// thread owns digits tid and tid + 256 — two status words per tile row of 512, two look-back walks interleaved in one
+// loop (LB_BATCH9 words each in flight) — and the per-warp histograms hold the two digits of a thread as the 16-bit
+// halves of one word (a tile has 4096 records, so neither the counts nor the tile-local offsets overflow a half):
+// zeroing, the scan over warps and the offset fold cost what they cost with 256 bins.
+template <typename KeyT, int BLOCK, int IPT, bool IOTA, bool AUX = false, int RB = 8>
 __global__ void __launch_bounds__(BLOCK, (sizeof(KeyT) == 4 && !AUX) ? BWTC_RS_MINB32 : BWTC_RS_MINB) k_radix_pass(const KeyT* __restrict__ keys_in,
                                                       const uint32_t* __restrict__ vals_in,
                                                       KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
@@ -603,15 +673,17 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(KeyT) == 4 && !AUX) ? BWTC_RS_M
   // bit pack_bits of the id, the dense code of the character PRECEDING the suffix — the top character of the
   // next key in the array — so the BWT emission of k_rerank needs no text gather at all.
   static_assert(BLOCK >= 256 && BLOCK % 32 == 0, "BLOCK must cover the 256 digit bins");
+  static_assert(RB == 8 || (RB == 9 && BLOCK == 256), "9-bit digits: two digits per thread of a 256-thread CTA");
   constexpr int TILE = BLOCK * IPT, WARPS = BLOCK / 32;
+  constexpr uint32_t BINS = 1u << RB, DMASK = BINS - 1u;
   static_assert(TILE <= 65536, "local positions are kept as uint16");
+  static_assert(RB == 8 || 2 * TILE < 65536, "9-bit digits: tile-local offsets live in 16-bit halves");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
   uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw + sizeof(KeyT) * TILE);  // ids staged beside the keys
   uint32_t* s_whist = s_vals + TILE;
   uint32_t* s_binbase = s_whist + WARPS * 256;
-  uint32_t* s_texcl = s_binbase + 256;
-  uint32_t* s_misc = s_texcl + 256;  // [0] tile id, [8..15] scan scratch
+  uint32_t* s_misc = s_binbase + BINS;  // [0] tile id, [8..23] scan scratch
   uint8_t* s_aux = reinterpret_cast<uint8_t*>(s_misc + 32);  // AUX: bytes staged beside keys and ids
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -680,7 +752,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(KeyT) == 4 && !AUX) ? BWTC_RS_M
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       const uint32_t g = first + 32 * k;
-      key[k] = (g < n) ? keys_in[g] : (KeyT)~(KeyT)0;  // pads: digit 255, last in index order
+      key[k] = (g < n) ? keys_in[g] : (KeyT)~(KeyT)0;  // pads: the last digit, last in index order
       val[k] = (g < n) ? (IOTA ? (iota_top - g) : vals_in[g]) : 0u;
       if (IOTA && pack_bits && g + 1u < n) val[k] |= ((uint32_t)(keys_in[g + 1u] >> topshift) & pred_mask) << pack_bits;
       if (AUX) {
@@ -706,24 +778,144 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(KeyT) == 4 && !AUX) ? BWTC_RS_M
   }
 #endif
   uint32_t cnt = 0, pub = 0;
-  uint32_t* my_status = status + (size_t)tile * 256u + (tid & 255);
+  uint32_t* my_status = status + (size_t)tile * BINS + (tid & 255);
   // ---- rank inside the warp
   uint16_t lpos[IPT];
   uint32_t* my_hist = s_whist + warp * 256;
   const uint32_t lt = lanemask_lt();
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
-    const uint32_t d = (uint32_t)(key[k] >> shift) & 0xFFu;
-    const uint32_t m = match_digit8(d);
+    const uint32_t d = (uint32_t)(key[k] >> shift) & DMASK;
+    uint32_t m;
+    if constexpr (RB == 9) m = match_digit9(d);
+    else m = match_digit8(d);
     const int leader = __ffs(m) - 1;
     uint32_t old = 0;
-    if (lane == leader) old = atomicAdd(&my_hist[d], (uint32_t)__popc(m));  // one shared-memory RMW, not LDS+STS
-    old = __shfl_sync(0xFFFFFFFFu, old, leader);
+    if constexpr (RB == 9) {
+      const uint32_t hs = (d >> 8) * 16u;  // digit d lives in half d >> 8 of word d & 255
+      if (lane == leader) old = atomicAdd(&my_hist[d & 255u], (uint32_t)__popc(m) << hs);
+      old = (__shfl_sync(0xFFFFFFFFu, old, leader) >> hs) & 0xFFFFu;
+    } else {
+      if (lane == leader) old = atomicAdd(&my_hist[d], (uint32_t)__popc(m));  // one shared-memory RMW, not LDS+STS
+      old = __shfl_sync(0xFFFFFFFFu, old, leader);
+    }
     lpos[k] = (uint16_t)(old + __popc(m & lt));
     __syncwarp();
   }
   __syncthreads();
   BWTC_PROF(4);
+  if constexpr (RB == 9) {
+    // ---- two digits per thread (tid -> low half, tid + 256 -> high half of every packed word)
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      const uint32_t t = s_whist[w * 256 + tid];
+      s_whist[w * 256 + tid] = run;
+      run += t;
+    }
+    const uint32_t cnt0 = run & 0xFFFFu, cnt1 = run >> 16;
+    const uint32_t pub0 = cnt0;
+    const uint32_t pub1 = cnt1 - ((tid == 255) ? ((uint32_t)TILE - valid) : 0u);  // pads (digit 511) are not records
+    const uint32_t first_flag = (tile == 0 ? LB_PREFIX : 0u);
+    st_relaxed_u32(my_status, first_flag | (pub0 + 1u));
+    st_relaxed_u32(my_status + 256, first_flag | (pub1 + 1u));
+    // tile-local exclusive offsets of both halves with ONE packed scan (every partial sum is <= TILE)
+    uint32_t tot_pk = 0, dummy0, dummy1;
+    uint32_t pk_excl;
+    scan256_excl2(run, 0u, s_misc + 8, pk_excl, dummy0, tot_pk, dummy1);
+    const uint32_t texcl0 = pk_excl & 0xFFFFu;
+    const uint32_t texcl1 = (pk_excl >> 16) + (tot_pk & 0xFFFFu);
+    uint32_t gexcl0, gexcl1, gtot0, gtot1;
+    scan256_excl2(ghist[tid], ghist[tid + 256], s_misc + 8, gexcl0, gexcl1, gtot0, gtot1);
+    gexcl1 += gtot0;
+    {
+      const uint32_t fold = texcl0 | (texcl1 << 16);
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) s_whist[w * 256 + tid] += fold;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t d = (uint32_t)(key[k] >> shift) & DMASK;
+      const uint32_t p = ((my_hist[d & 255u] >> ((d >> 8) * 16u)) & 0xFFFFu) + lpos[k];
+      s_keys[p] = key[k];
+      s_vals[p] = val[k];
+      if (AUX) s_aux[p] = (uint8_t)(aux[k / 4] >> (8 * (k % 4)));
+    }
+    BWTC_PROF(5);
+    // ---- decoupled look-back of both digits, interleaved: LB_BATCH9 words of each in flight per round trip
+    uint32_t excl0 = 0, excl1 = 0;
+    if (tile != 0) {
+      long long t0 = (long long)tile - 1, t1 = t0;
+      uint32_t spins = 0;
+      uint32_t live0 = 0xFFFFFFFFu, live1 = 0xFFFFFFFFu;  // all-ones while the digit's walk is not finished
+      while (live0 | live1) {
+        uint32_t v0[LB_BATCH9], v1[LB_BATCH9];
+        const uint32_t* row0 = status + t0 * (long long)BINS + tid;
+        const uint32_t* row1 = status + t1 * (long long)BINS + 256 + tid;
+#pragma unroll
+        for (int i = 0; i < LB_BATCH9; ++i) v0[i] = ld_relaxed_u32(row0 - i * (int)BINS);
+#pragma unroll
+        for (int i = 0; i < LB_BATCH9; ++i) v1[i] = ld_relaxed_u32(row1 - i * (int)BINS);
+        uint32_t alive0 = live0, alive1 = live1, fin0 = 0, fin1 = 0;
+        int c0 = 0, c1 = 0;
+#pragma unroll
+        for (int i = 0; i < LB_BATCH9; ++i) {
+          {
+            const uint32_t pubd = (uint32_t)((int32_t)(v0[i] | (0u - v0[i])) >> 31);
+            const uint32_t ispre = (uint32_t)((int32_t)v0[i] >> 31);
+            const uint32_t isagg = pubd & ~ispre;
+            excl0 += ((v0[i] & LB_VALUE) - 1u) & alive0 & pubd;
+            fin0 |= alive0 & ispre;
+            c0 += (int)(alive0 & isagg & 1u);
+            alive0 &= isagg;
+          }
+          {
+            const uint32_t pubd = (uint32_t)((int32_t)(v1[i] | (0u - v1[i])) >> 31);
+            const uint32_t ispre = (uint32_t)((int32_t)v1[i] >> 31);
+            const uint32_t isagg = pubd & ~ispre;
+            excl1 += ((v1[i] & LB_VALUE) - 1u) & alive1 & pubd;
+            fin1 |= alive1 & ispre;
+            c1 += (int)(alive1 & isagg & 1u);
+            alive1 &= isagg;
+          }
+        }
+        live0 &= ~fin0;  // fin is all-ones once the walk met an inclusive prefix
+        live1 &= ~fin1;
+        t0 -= c0;
+        t1 -= c1;
+        if ((live0 | live1) && c0 + c1 == 0) {
+          ++spins;
+          if (spins > g_lb_spin_limit || ((spins & 255u) == 0u && ld_relaxed_u32(ctrl + CTR_ERR))) {
+            atomicExch(&ctrl[CTR_ERR], 1u);
+            break;
+          }
+          __nanosleep(20);
+        }
+      }
+      st_relaxed_u32(my_status, LB_PREFIX | ((excl0 + pub0 + 1u) & LB_VALUE));
+      st_relaxed_u32(my_status + 256, LB_PREFIX | ((excl1 + pub1 + 1u) & LB_VALUE));
+    }
+    s_binbase[tid] = gexcl0 + excl0 - texcl0;
+    s_binbase[tid + 256] = gexcl1 + excl1 - texcl1;
+    __syncthreads();
+    BWTC_PROF(6);
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const uint32_t p = tid + k * BLOCK;
+      const KeyT kk = s_keys[p];
+      const uint32_t vv = s_vals[p];
+      const uint32_t d = (uint32_t)(kk >> shift) & DMASK;
+      const uint32_t g = s_binbase[d] + p;
+      if (p < valid) {
+        BWTC_ST(keys_out + g, kk);
+        BWTC_ST(vals_out + g, vv);
+        if (AUX) aux_out[g] = s_aux[p];
+      }
+    }
+    BWTC_PROF(8);
+    return;
+  }
 
   // ---- per-digit: exclusive scan over warps; tile-local and global exclusive digit offsets
   if (tid < 256) {
@@ -1571,12 +1763,13 @@ __global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restr
                                                          const uint32_t* __restrict__ rank, uint32_t N, uint32_t h,
                                                          int lo_bits, unsigned long long* __restrict__ keys,
                                                          uint32_t* __restrict__ idx, uint32_t* __restrict__ hist,
-                                                         int npass, const uint32_t* __restrict__ ctrl) {
-  __shared__ uint32_t s_hist[8 * 256];
+                                                         int npass, const uint32_t* __restrict__ ctrl, uint32_t rb) {
+  __shared__ uint32_t s_hist[8 * 512];
   const int tid = threadIdx.x;
+  const uint32_t dmask = (1u << rb) - 1u;
   if (ctrl[CTR_ERR]) return;
 #pragma unroll
-  for (int p = 0; p < 8; ++p) s_hist[p * 256 + tid] = 0;
+  for (int p = 0; p < 16; ++p) s_hist[p * 256 + tid] = 0;
   __syncthreads();
   for (uint32_t j = blockIdx.x * blockDim.x + tid; j < m; j += gridDim.x * blockDim.x) {
     const uint32_t i = list[j];
@@ -1585,13 +1778,14 @@ __global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restr
     const unsigned long long key = ((unsigned long long)(r >> 1) << lo_bits) | (unsigned long long)r2;  // see k_build_keys
     keys[j] = key;
     idx[j] = i | ((r & 1u) << 31);
-    for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p * 256 + (uint32_t)((key >> (8 * p)) & 0xFF)], 1u);
+    for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[(p << rb) + ((uint32_t)(key >> (rb * p)) & dmask)], 1u);
   }
   __syncthreads();
-  for (int p = 0; p < npass; ++p) {
-    const uint32_t v = s_hist[p * 256 + tid];
-    if (v) atomicAdd(&hist[p * 256 + tid], v);
-  }
+  for (int p = 0; p < npass; ++p)
+    for (uint32_t e = tid; e <= dmask; e += 256) {
+      const uint32_t v = s_hist[(p << rb) + e];
+      if (v) atomicAdd(&hist[(p << rb) + e], v);
+    }
 }
 
 // =====================================================================================================

@@ -110,6 +110,32 @@ def test_any_round0_key_shape_gives_identical_bytes(ctx, oracle, force):
     assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
 
 
+@pytest.mark.parametrize("radix9", ["1", "0"])
+@pytest.mark.parametrize("kind,chars", [("markov", 6), ("markov", 7), ("markov", 8), ("markov", 9), ("markov", 10),
+                                        ("dna", 17), ("dna", 22), ("dna", 27), ("dna", 31), ("dna", 32),
+                                        ("random", 5), ("random", 8)])
+def test_digit_width_of_the_radix_passes(oracle, monkeypatch, radix9, kind, chars):
+    """64-bit keys of 34..64 used bits: with BWTC_RADIX9=1 (an experiment, measured slower, default off) 9-bit digits are
+    chosen whenever they save a pass over 8-bit digits (36 bits: 4 instead of 5 passes, ... 60 bits: 7 instead of 8; 48 and
+    64 bits: 8-bit digits stay).  Same bytes either way, and
+    the pass count of round 0 shows which width ran.  A size with a ragged last tile and >= 2 tiles per CTA wave."""
+    monkeypatch.setenv("BWTC_RADIX9", radix9)
+    n = 700001
+    x = bw.generate(kind, n, seed=29)
+    want = oracle.block(x, 8)
+    c = bw.CudaContext(n + 1)
+    c.set_round0(chars, 8)
+    try:
+        got = _gpu_block(c, x, 8)
+        st = c.stats()
+    finally:
+        c.close()
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all() and (got[2] == want[2]).all()
+    bits = {"markov": 6, "dna": 2, "random": 8}[kind] * chars
+    p8, p9 = -(-bits // 8), -(-bits // 9)
+    assert st["passes"][0] == (p9 if (radix9 == "1" and p9 < p8) else p8), (bits, st["passes"][:2])
+
+
 @pytest.mark.parametrize("force", [(0, 0), (1, 4), (3, 4), (2, 8), (5, 8), (64, 8)])
 @pytest.mark.parametrize("kind", ["markov", "dna", "zeros"])
 def test_lazy_ranks_with_any_key_shape(oracle, monkeypatch, force, kind):
@@ -285,6 +311,10 @@ ENGINE_KNOBS = [
     {"BWTC_LAZY": "2", "BWTC_PACK_PRED": "0", "BWTC_AUX_MIN_MIB": "0"},
     {"BWTC_LAZY": "2", "BWTC_RERANK_WINDOW_MB": "1"},                # the fallback materialises ranks through the bucketed scatter
     {"BWTC_LAZY": "2", "BWTC_LADDER_FIRST": "0"},
+    {"BWTC_RADIX9": "1"},                                            # 9-bit digit passes where they save a pass (experiment, default off)
+    {"BWTC_RADIX9": "1", "BWTC_SEG": "0"},                           # ... in the doubling rounds too
+    {"BWTC_RADIX9": "1", "BWTC_SEG": "0", "BWTC_STATIC_TILES": "0"},  # ... with tile tickets
+    {"BWTC_RADIX9": "1", "BWTC_PACK_PRED": "0", "BWTC_AUX_MIN_MIB": "0"},  # ... carrying the one-byte payload
 ]
 
 
