@@ -1589,8 +1589,8 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   ALLOC(c->d_text, padded);
   ALLOC(c->d_out, padded);
   ALLOC(c->d_rank, (N + 64) * 4);
-  ALLOC(c->d_keys[0], N * 8);
-  ALLOC(c->d_keys[1], N * 8);
+  ALLOC(c->d_keys[0], N * 8 + 64);  // (+ one sector: rank_lookup reads whole 32-byte sectors of the sorted keys)
+  ALLOC(c->d_keys[1], N * 8 + 64);
   ALLOC(c->d_idx[0], N * 4);
   ALLOC(c->d_idx[1], N * 4);
   ALLOC(c->d_zero, (size_t)(CTR_WORDS + HIST_WORDS) * 4 + (size_t)MAX_RERANK_WINDOWS * c->max_aux_tiles * 8 + 64);
@@ -1674,7 +1674,7 @@ uint64_t bwtc_cuda_scratch_bytes(uint32_t max_block_bytes) {
   const uint64_t padded = ((N + TEXT_PAD + 15) / 16) * 16 + 16;
   uint64_t b = 5 * padded;                                  // d_in, d_text, d_out, d_aux[2]
   b += (N + 64) * 4;                                        // d_rank
-  b += 2 * N * 8 + 2 * N * 4;                               // d_keys[2], d_idx[2]
+  b += 2 * (N * 8 + 64) + 2 * N * 4;                        // d_keys[2], d_idx[2]
   b += N * 4 + 64;                                          // d_scat
   b += (uint64_t)(CTR_WORDS + HIST_WORDS) * 4 + (uint64_t)MAX_RERANK_WINDOWS * aux_tiles * 8 + 64;  // d_zero
   b += (uint64_t)MAX_PASSES * (rs_tiles + LB_PAD_ROWS) * status_row_words_for(env_radix9()) * 4u;     // d_status

@@ -1077,6 +1077,47 @@ struct LookupParams {
   uint8_t lut[256];
 };
 
+// Lower bound of `key` in sorted[lo, hi) reading whole 32-byte sectors: the first probe is INTERPOLATED from the key bits
+// below the table prefix (inside one table bucket they are close to uniform), then the search walks to the neighbouring
+// sector twice before it falls back to bisection.  A bucket of ~32 keys costs 1-2 DRAM sectors instead of the ~3 distinct
+// ones of a plain binary search (the look-ups are bound by random DRAM sectors).  The key array is padded to a sector.
+template <typename KeyT>
+__device__ __forceinline__ uint32_t sector_lower_bound(const KeyT* __restrict__ sk, KeyT key, uint32_t lo, uint32_t hi,
+                                                       uint32_t frac16) {
+  constexpr uint32_t KPS = 32 / sizeof(KeyT);  // keys per sector
+  uint32_t g = lo + (uint32_t)(((unsigned long long)(hi - lo) * frac16) >> 16);
+  for (int it = 0; lo < hi; ++it) {
+    if (g >= hi) g = hi - 1u;
+    if (g < lo) g = lo;
+    const uint32_t s = g & ~(KPS - 1u);
+    KeyT v[KPS];
+    if constexpr (sizeof(KeyT) == 8) {
+      const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(sk + s);
+      const ulonglong2 y = *reinterpret_cast<const ulonglong2*>(sk + s + 2);
+      v[0] = (KeyT)x.x; v[1] = (KeyT)x.y; v[2] = (KeyT)y.x; v[3] = (KeyT)y.y;
+    } else {
+      const uint4 x = *reinterpret_cast<const uint4*>(sk + s);
+      const uint4 y = *reinterpret_cast<const uint4*>(sk + s + 4);
+      v[0] = (KeyT)x.x; v[1] = (KeyT)x.y; v[2] = (KeyT)x.z; v[3] = (KeyT)x.w;
+      v[4] = (KeyT)y.x; v[5] = (KeyT)y.y; v[6] = (KeyT)y.z; v[7] = (KeyT)y.w;
+    }
+    const uint32_t a = s > lo ? s : lo, b = (s + KPS < hi) ? s + KPS : hi;  // valid entries of this sector
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < KPS; ++q) c += (s + q >= a && s + q < b && v[q] < key) ? 1u : 0u;
+    if (c == 0u) {            // nothing below the key here: the bound is at or left of a
+      hi = a;
+      g = (it < 2) ? (a ? a - 1u : 0u) : lo + ((hi - lo) >> 1);
+    } else if (c == b - a) {  // everything here is below the key: the bound is at or right of b
+      lo = b;
+      g = (it < 2) ? b : lo + ((hi - lo) >> 1);
+    } else {
+      return a + c;
+    }
+  }
+  return lo;
+}
+
 // rank of suffix j (without the DONE flag).
 __device__ __forceinline__ uint32_t rank_lookup(const LookupParams& lk, const uint32_t* __restrict__ rank, uint32_t j) {
   if (!lk.enabled || ((lk.livebits[j >> 5] >> (j & 31u)) & 1u)) return rank[j] & RANK_MASK;
@@ -1087,6 +1128,14 @@ __device__ __forceinline__ uint32_t rank_lookup(const LookupParams& lk, const ui
   }
   const uint32_t p = (uint32_t)(key >> lk.tshift);
   uint32_t lo = lk.ktab[p], hi = lk.ktab[p + 1u];
+#ifndef BWTC_LAZY_BINSEARCH
+  // the 16 key bits below the table prefix, as a fraction of the bucket
+  const uint32_t frac16 = lk.tshift >= 16u ? (uint32_t)(key >> (lk.tshift - 16u)) & 0xFFFFu
+                                           : ((uint32_t)key << (16u - lk.tshift)) & 0xFFFFu;
+  if (lk.keybytes == 8u)
+    return sector_lower_bound<unsigned long long>(static_cast<const unsigned long long*>(lk.sorted_keys), key, lo, hi, frac16);
+  return sector_lower_bound<uint32_t>(static_cast<const uint32_t*>(lk.sorted_keys), (uint32_t)key, lo, hi, frac16);
+#else
   if (lk.keybytes == 8u) {
     const unsigned long long* sk = static_cast<const unsigned long long*>(lk.sorted_keys);
     while (lo < hi) {  // lower bound: the key is unique (singleton), so this is its position
@@ -1102,6 +1151,7 @@ __device__ __forceinline__ uint32_t rank_lookup(const LookupParams& lk, const ui
     }
   }
   return lo;
+#endif
 }
 
 // ktab holds the first sorted position of every key prefix that occurs (k_rerank, lazy) and 0xFFFFFFFF elsewhere; fill the
@@ -1805,8 +1855,11 @@ __global__ void __launch_bounds__(256) k_build_from_list(const uint32_t* __restr
 
 // Persistent grid: tile t = blockIdx.x, blockIdx.x + gridDim.x, ... while t * SEG_T < m (m is read from the
 // device-side LadderState, so the host can enqueue the round before it knows how many suffixes are live).
+#ifndef BWTC_SEG_MINB_LAZY
+#define BWTC_SEG_MINB_LAZY 4  // (3 CTAs/SM with 80 registers measured the same)
+#endif
 template <bool LAZY>
-__global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const LadderState* __restrict__ st, PoolPtrs pool,
+__global__ void __launch_bounds__(256, LAZY ? BWTC_SEG_MINB_LAZY : BWTC_SEG_MINB) k_seg_round(const LadderState* __restrict__ st, PoolPtrs pool,
                                                    const uint32_t* __restrict__ rank, uint32_t N, EmitParams ep,
                                                    uint32_t* __restrict__ ctrl, const LookupParams* __restrict__ lkp) {
   constexpr int IPT = SEG_CAP / 256;
@@ -1892,6 +1945,8 @@ __global__ void __launch_bounds__(256, BWTC_SEG_MINB) k_seg_round(const LadderSt
         if (((livemask >> k) & 1u) && h < N - myid[k]) lo[k] = (rank[myid[k] + h] & RANK_MASK) + 1u;
       }
     } else {  // lazy ranks: a singleton's rank is found in the sorted round-0 keys (LookupParams live in global memory)
+      // (one search after the other: running the IPT searches of a thread in lockstep, IPT independent loads per step, was
+      // measured SLOWER — the look-ups are bound by random DRAM sectors, not by the dependent chain: r02_experiments.md)
 #pragma unroll
       for (int k = 0; k < IPT; ++k) {
         lo[k] = 0;
