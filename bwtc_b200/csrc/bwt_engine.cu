@@ -130,10 +130,11 @@ struct bwtc_cuda_ctx {
                                   // slower (a 9-bit pass costs +23%, 7 of them more than 8 eight-bit ones): kept as an
                                   // experiment, profiles/r02_experiments.md
   uint32_t status_row_words = 256;
-  int use_lazy = 1;               // lazy ranks after round 0: 0 never, 1 when a sample of the sorted keys says
-                                  // few suffixes stay in groups, 2 always (tests)
+  int use_lazy = 1;               // lazy ranks after round 0: 0 never, 1 when the key-shape policy predicts
+                                  // that few suffixes stay in groups, 2 always (tests)
   uint32_t lazy_min_suffixes = 4u << 20;
-  double lazy_max_live = 0.025;
+  double lazy_max_live = 0.065;   // measured break-even with the sector look-ups: -15..-19% at 3%, -10..-12% at 4.6%, -4% at 6%,
+                                  // +-1% at 9% predicted live (DNA / random bytes, 128..384 MiB)
   int use_seg = 1;                // segmented (sort-free) doubling rounds when every group is small
   int use_batch = 1;              // small equal-sized blocks of one call are sorted as one text
   int use_pack_pred = 1;          // carry code(T[id-1]) above the id through the round-0 sort when it fits
