@@ -130,6 +130,7 @@ struct bwtc_cuda_ctx {
                                   // slower (a 9-bit pass costs +23%, 7 of them more than 8 eight-bit ones): kept as an
                                   // experiment, profiles/r02_experiments.md
   uint32_t status_row_words = 256;
+  uint32_t rerank_pf_tiles = 0;   // k_rerank: L2 prefetch distance in tiles (BWTC_RERANK_PF; 0 = off)
   int use_lazy = 1;               // lazy ranks after round 0: 0 never, 1 when the key-shape policy predicts
                                   // that few suffixes stay in groups, 2 always (tests)
   uint32_t lazy_min_suffixes = 4u << 20;
@@ -440,6 +441,8 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
     const uint32_t win_ids = div_up(N, nwin);
     rp.win_lo = 0;
     rp.win_hi = 0xFFFFFFFFu;
+    rp.emit = 1;
+    rp.pf_tiles = ctx->rerank_pf_tiles;
     rp.ctr_slot = tile_slot(ctx, (uint32_t)CTR_RERANK);
     rp.nbuckets = nwin;
     rp.bucket_magic = (uint32_t)(((1ull << 32) + win_ids - 1) / win_ids);
@@ -459,6 +462,8 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
   for (uint32_t w = 0; w < nwin; ++w) {
     rp.win_lo = (uint32_t)((uint64_t)N * w / nwin);
     rp.win_hi = (w + 1 == nwin) ? 0xFFFFFFFFu : (uint32_t)((uint64_t)N * (w + 1) / nwin);
+    rp.emit = ROUND0 ? (w == 0 ? 1u : 2u) : 0u;  // round 0: the first window launch emits every BWT byte (whole words)
+    rp.pf_tiles = ctx->rerank_pf_tiles;
     rp.ctr_slot = tile_slot(ctx, (uint32_t)(CTR_RERANK + w));
     rp.nbuckets = 0;
     rp.bucket_magic = 0;
@@ -1544,6 +1549,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (const char* e = getenv("BWTC_LADDER_FIRST")) c->ladder_first = std::max(0, atoi(e));
   if (const char* e = getenv("BWTC_LADDER_MORE")) c->ladder_more = std::max(1, atoi(e));
   if (const char* e = getenv("BWTC_LAZY")) c->use_lazy = atoi(e);
+  if (const char* e = getenv("BWTC_RERANK_PF")) c->rerank_pf_tiles = (uint32_t)std::max(0, atoi(e));
   c->use_radix9 = env_radix9();
   c->status_row_words = status_row_words_for(c->use_radix9);
   if (const char* e = getenv("BWTC_LAZY_MIN_MIB")) c->lazy_min_suffixes = (uint32_t)std::max(0L, atol(e)) << 20;

@@ -1060,6 +1060,12 @@ struct RerankParams {
   // rank is its sorted position and is looked up in the retained sorted keys when somebody needs it (rank_lookup).
   // 2 = materialise: write rank[] for the singletons only (the fallback out of lazy mode; nothing else is touched).
   uint32_t lazy;
+  // ROUND0: which records this launch emits BWT bytes for — 0: those whose id is in [win_lo, win_hi); 1: all (the first
+  // launch of a windowed scatter, so a thread's eight consecutive output bytes leave as one store); 2: none.
+  uint32_t emit;
+  // > 0: every CTA first asks L2 for the records of tile (mine + pf_tiles) — the tile a CTA launched about one wave later
+  // will load; the kernel is bound by the latency of its up-front record loads (ncu: 49% of stall samples on their first use)
+  uint32_t pf_tiles;
   uint32_t* livebits;
   uint32_t* ktab;
   uint32_t tshift;          // key >> tshift = table index
@@ -1312,6 +1318,17 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
   const uint32_t tile_base = tile * (uint32_t)TILE;
   if (tile_base >= m) return;
   const uint32_t j0 = tile_base + tid * IPT;
+  if (rp.pf_tiles) {
+    const unsigned long long pbase = ((unsigned long long)tile + rp.pf_tiles) * (unsigned long long)TILE;
+    if (pbase + TILE <= (unsigned long long)m) {
+      constexpr int KLINES = TILE * (int)sizeof(KeyT) / 128, ILINES = TILE * 4 / 128;  // 128 / 64 (u64) or 64 / 64 lines
+      const char* p = nullptr;
+      if (tid < KLINES) p = reinterpret_cast<const char*>(keys + pbase) + (size_t)tid * 128;
+      else if (tid < KLINES + ILINES) p = reinterpret_cast<const char*>(idx + pbase) + (size_t)(tid - KLINES) * 128;
+      else if (ROUND0 && rp.packed == 2u && tid < KLINES + ILINES + TILE / 128) p = reinterpret_cast<const char*>(rp.pred_aux + pbase) + (size_t)(tid - KLINES - ILINES) * 128;
+      if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
 
   KeyT key[IPT];
   uint32_t id[IPT];
@@ -1519,6 +1536,7 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
   const bool bucketed = rp.nbuckets > 1;
   uint32_t live = 0, livemask = 0, gmax = 0, nrv[IPT];
   uint32_t wrmask = 0, bpos[IPT];
+  uint32_t embits = 0, ew0 = 0, ew1 = 0;  // ROUND0: the BWT bytes of my eight (consecutive) sorted positions
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
     const uint32_t j = j0 + k;
@@ -1540,11 +1558,17 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
         changed = (HF != HH);
       }
       const bool in_win = (id[k] >= rp.win_lo) && (id[k] < rp.win_hi);
-      if (single && in_win && !owns_hole(ep, id[k]) && !(LAZY && rp.lazy == 2u)) {  // emit L[nr] = T[id-1]
+      const bool emit_here = ROUND0 ? (rp.emit == 1u || (rp.emit == 0u && in_win)) : in_win;
+      if (single && emit_here && !owns_hole(ep, id[k]) && !(LAZY && rp.lazy == 2u)) {  // emit L[nr] = T[id-1]
         uint8_t ch;
         if (ROUND0 && rp.packed) ch = s_dec[((k < 4 ? pc0 >> (8 * k) : pc1 >> (8 * (k - 4)))) & 0xFFu];
         else ch = ep.text[id[k] - 1];
-        emit_bwt(ep, nr, ch);
+        if (ROUND0) {  // nr == j: collected, stored after the loop
+          embits |= 1u << k;
+          if (k < 4) ew0 |= (uint32_t)ch << (8 * k); else ew1 |= (uint32_t)ch << (8 * (k - 4));
+        } else {
+          emit_bwt(ep, nr, ch);
+        }
       }
       if (single) nr |= RANK_DONE;
       else if (sp.enable) { ++live; livemask |= 1u << k; gmax = max(gmax, j - HF + 1u); }
@@ -1572,6 +1596,37 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
         } else {
           rank[id[k]] = nr;
         }
+      }
+    }
+  }
+  if (ROUND0 && embits) {
+    // A singleton's rank is its sorted position, so my eight records are the output bytes j0 .. j0+7: one 8-byte (or
+    // 4-byte) store when all of them are emitted, instead of byte stores that touch eight sectors per warp instruction.
+    // `plain`: none of the eight positions is the parked last byte of a block (emit_bwt) and the buffer is aligned.
+    bool plain = (reinterpret_cast<uintptr_t>(ep.out) & 7u) == 0u;
+    if (ep.nblocks <= 1u) {
+      plain = plain && !(ep.block_mode && j0 + 8u > ep.N - 1u);
+    } else {
+      const uint32_t kb = j0 / ep.stride;
+      const uint32_t last = ((kb + 1u == ep.nblocks) ? ep.N : (kb + 1u) * ep.stride) - 1u;
+      plain = plain && (j0 + 7u < last);
+    }
+    if (plain && embits == 0xFFu) {
+      *reinterpret_cast<uint2*>(ep.out + j0) = make_uint2(ew0, ew1);
+    } else {
+      if (plain && (embits & 0xFu) == 0xFu) {
+        *reinterpret_cast<uint32_t*>(ep.out + j0) = ew0;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if ((embits >> k) & 1u) emit_bwt(ep, j0 + k, (uint8_t)(ew0 >> (8 * k)));
+      }
+      if (plain && (embits & 0xF0u) == 0xF0u) {
+        *reinterpret_cast<uint32_t*>(ep.out + j0 + 4) = ew1;
+      } else {
+#pragma unroll
+        for (int k = 4; k < 8; ++k)
+          if ((embits >> k) & 1u) emit_bwt(ep, j0 + k, (uint8_t)(ew1 >> (8 * (k - 4))));
       }
     }
   }
