@@ -130,6 +130,8 @@ struct bwtc_cuda_ctx {
                                   // slower (a 9-bit pass costs +23%, 7 of them more than 8 eight-bit ones): kept as an
                                   // experiment, profiles/r02_experiments.md
   uint32_t status_row_words = 256;
+  int hybrid2 = 0;                // BWTC_HYBRID2=1: with two L2 windows, window 0 is written directly and window 1 staged + one
+                                  // k_scatter_bucket, instead of one k_rerank launch per window (measured equal: 2.90 vs 2.88 ms)
   uint32_t rerank_pf_tiles = 0;   // k_rerank: L2 prefetch distance in tiles (BWTC_RERANK_PF; 0 = off)
   int use_lazy = 1;               // lazy ranks after round 0: 0 never, 1 when the key-shape policy predicts
                                   // that few suffixes stay in groups, 2 always (tests)
@@ -437,7 +439,8 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
   const uint32_t nwin = single_window ? 1u : rerank_windows(ctx, N, m);
   const KeyT* keys = static_cast<const KeyT*>(ctx->d_keys[cur]);
   uint32_t* woff = ctx->d_tilecnt + 2 * ctx->max_aux_tiles;
-  if (ctx->bucket_min_windows && nwin >= (uint32_t)ctx->bucket_min_windows) {
+  const bool hybrid2 = ctx->hybrid2 && nwin == 2u && !(ROUND0 && rp.lazy);
+  if ((ctx->bucket_min_windows && nwin >= (uint32_t)ctx->bucket_min_windows) || hybrid2) {
     const uint32_t win_ids = div_up(N, nwin);
     rp.win_lo = 0;
     rp.win_hi = 0xFFFFFFFFu;
@@ -445,6 +448,7 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
     rp.pf_tiles = ctx->rerank_pf_tiles;
     rp.ctr_slot = tile_slot(ctx, (uint32_t)CTR_RERANK);
     rp.nbuckets = nwin;
+    rp.direct0 = hybrid2 ? 1u : 0u;
     rp.bucket_magic = (uint32_t)(((1ull << 32) + win_ids - 1) / win_ids);
     StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, no_stage ? 0 : 1, ctx->d_idx[cur ^ 1], ctx->d_scat, woff};
     if (ROUND0 && rp.lazy)
@@ -452,11 +456,11 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
     else
       k_rerank<KeyT, ROUND0><<<tiles, 256, 0, st>>>(keys, ctx->d_idx[cur], ctx->d_rank, rp, ctx->d_tstate(), ctx->d_ctrl(), ep, sp);
     const uint32_t grid = std::min<uint32_t>(div_up(tiles, 8), (uint32_t)ctx->sm_count * 8u);
-    for (uint32_t b = 0; b < nwin; ++b)
+    for (uint32_t b = hybrid2 ? 1u : 0u; b < nwin; ++b)
       k_scatter_bucket<<<grid, 256, 0, st>>>(ctx->d_idx[cur ^ 1], ctx->d_scat, woff, tiles, nwin, b, AUX_TILE, ctx->d_rank, ctx->d_ctrl());
     CK(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches += 1 + nwin;
-    ctx->stats.algorithmic_bytes += (uint64_t)m * 16;  // staged (id, rank) pairs: written once, read once
+    ctx->stats.kernel_launches += 1 + nwin - (hybrid2 ? 1u : 0u);
+    ctx->stats.algorithmic_bytes += (uint64_t)m * (hybrid2 ? 8 : 16);  // staged (id, rank) pairs: written once, read once
     return 0;
   }
   for (uint32_t w = 0; w < nwin; ++w) {
@@ -466,6 +470,7 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
     rp.pf_tiles = ctx->rerank_pf_tiles;
     rp.ctr_slot = tile_slot(ctx, (uint32_t)(CTR_RERANK + w));
     rp.nbuckets = 0;
+    rp.direct0 = 0;
     rp.bucket_magic = 0;
     StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, (w == 0 && !no_stage) ? 1 : 0, nullptr, nullptr, nullptr};
     if (ROUND0 && rp.lazy)
@@ -1549,6 +1554,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (const char* e = getenv("BWTC_LADDER_FIRST")) c->ladder_first = std::max(0, atoi(e));
   if (const char* e = getenv("BWTC_LADDER_MORE")) c->ladder_more = std::max(1, atoi(e));
   if (const char* e = getenv("BWTC_LAZY")) c->use_lazy = atoi(e);
+  if (const char* e = getenv("BWTC_HYBRID2")) c->hybrid2 = atoi(e);
   if (const char* e = getenv("BWTC_RERANK_PF")) c->rerank_pf_tiles = (uint32_t)std::max(0, atoi(e));
   c->use_radix9 = env_radix9();
   c->status_row_words = status_row_words_for(c->use_radix9);

@@ -1055,6 +1055,9 @@ struct RerankParams {
   uint8_t decode[256];      // dense code -> byte (packed emission)
   uint32_t nbuckets;        // > 1: bucketed scatter — instead of writing rank[] the tile stages its (id, rank) pairs
   uint32_t bucket_magic;    //      grouped by id bucket (bucket = min(umulhi(id, magic), nbuckets-1)); see k_scatter_bucket
+  uint32_t direct0;         // bucketed: ids of bucket 0 are written to rank[] directly (its window stays L2-resident during
+                            // this launch), only the other buckets are staged — the two-window case: one pass over the
+                            // records + one k_scatter_bucket over half of the pairs, instead of two passes over the records
   // ROUND0, lazy ranks: 1 = rank[] is written only for suffixes that stay in a group (and the few "short"
   // ones), their bit is set in livebits, and the first sorted position of every key prefix goes to ktab; a singleton's
   // rank is its sorted position and is looked up in the retained sorted keys when somebody needs it (rank_lookup).
@@ -1318,18 +1321,6 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
   const uint32_t tile_base = tile * (uint32_t)TILE;
   if (tile_base >= m) return;
   const uint32_t j0 = tile_base + tid * IPT;
-  if (rp.pf_tiles) {
-    const unsigned long long pbase = ((unsigned long long)tile + rp.pf_tiles) * (unsigned long long)TILE;
-    if (pbase + TILE <= (unsigned long long)m) {
-      constexpr int KLINES = TILE * (int)sizeof(KeyT) / 128, ILINES = TILE * 4 / 128;  // 128 / 64 (u64) or 64 / 64 lines
-      const char* p = nullptr;
-      if (tid < KLINES) p = reinterpret_cast<const char*>(keys + pbase) + (size_t)tid * 128;
-      else if (tid < KLINES + ILINES) p = reinterpret_cast<const char*>(idx + pbase) + (size_t)(tid - KLINES) * 128;
-      else if (ROUND0 && rp.packed == 2u && tid < KLINES + ILINES + TILE / 128) p = reinterpret_cast<const char*>(rp.pred_aux + pbase) + (size_t)(tid - KLINES - ILINES) * 128;
-      if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
-  }
-
   KeyT key[IPT];
   uint32_t id[IPT];
   if (tile_base + TILE <= m) {  // full tile: 128-bit loads (buffers are 256-byte aligned, j0 % 8 == 0)
@@ -1364,6 +1355,22 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
     }
   }
   if (err_at_entry) return;
+  // (issued once my own record loads have landed: the DRAM queue is idle while the resident CTAs scan)
+  if (rp.pf_tiles) {
+    const unsigned long long pbase = ((unsigned long long)tile + rp.pf_tiles) * (unsigned long long)TILE;
+    if (pbase + TILE <= (unsigned long long)m) {
+      constexpr int KLINES = TILE * (int)sizeof(KeyT) / 128, ILINES = TILE * 4 / 128;  // 128 / 64 (u64) or 64 / 64 lines
+      const char* p = nullptr;
+      if (tid < KLINES) p = reinterpret_cast<const char*>(keys + pbase) + (size_t)tid * 128;
+      else if (tid < KLINES + ILINES) p = reinterpret_cast<const char*>(idx + pbase) + (size_t)(tid - KLINES) * 128;
+      else if (ROUND0 && rp.packed == 2u && tid < KLINES + ILINES + TILE / 128) p = reinterpret_cast<const char*>(rp.pred_aux + pbase) + (size_t)(tid - KLINES - ILINES) * 128;
+      // the address is made to depend on my last loaded record (an opaque "and 0"), so the prefetch issues behind the loads
+      uint32_t zero;
+      asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"((uint32_t)key[IPT - 1] ^ id[IPT - 1]));
+      if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + zero));
+    }
+  }
+
   uint32_t pc0 = 0, pc1 = 0;  // packed predecessor codes of the 8 records (one byte each)
   if (ROUND0 && rp.packed == 2u) {
     if (tile_base + TILE <= m) {
@@ -1591,8 +1598,12 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
       if (wr) {
         if (bucketed) {
           const uint32_t b = min(__umulhi(id[k], rp.bucket_magic), rp.nbuckets - 1u);
-          bpos[k] = atomicAdd(&s_bcnt[b], 1u);
-          wrmask |= 1u << k;
+          if (rp.direct0 && b == 0u) {
+            rank[id[k]] = nr;
+          } else {
+            bpos[k] = atomicAdd(&s_bcnt[b], 1u);
+            wrmask |= 1u << k;
+          }
         } else {
           rank[id[k]] = nr;
         }

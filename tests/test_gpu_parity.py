@@ -296,7 +296,10 @@ ENGINE_KNOBS = [
     {},                                                              # defaults
     {"BWTC_RERANK_WINDOW_MB": "1"},                                  # >= 3 id windows at 1-2 MiB: bucketed rank scatter
     {"BWTC_RERANK_WINDOW_MB": "1", "BWTC_BUCKET_MIN_WINDOWS": "0"},  # one k_rerank launch per id window
-    {"BWTC_RERANK_WINDOW_MB": "4", "BWTC_BUCKET_MIN_WINDOWS": "2"},  # bucketed scatter with exactly two buckets
+    {"BWTC_RERANK_WINDOW_MB": "4", "BWTC_BUCKET_MIN_WINDOWS": "2"},  # bucketed scatter from two windows on
+    {"BWTC_RERANK_WINDOW_MB": "6"},                                  # exactly two windows: one k_rerank launch per window
+    {"BWTC_RERANK_WINDOW_MB": "6", "BWTC_HYBRID2": "1"},             # ... or window 0 direct, window 1 staged (experiment, off)
+    {"BWTC_RERANK_WINDOW_MB": "6", "BWTC_HYBRID2": "1", "BWTC_SEG": "0"},  # the hybrid scatter in doubling rounds too
     {"BWTC_PACK_PRED": "0"},                                         # BWT characters gathered from the text
     {"BWTC_PACK_PRED": "0", "BWTC_AUX_MIN_MIB": "0"},                # predecessor codes as a one-byte payload array
     {"BWTC_PACK_PRED": "0", "BWTC_AUX_MIN_MIB": "0", "BWTC_RERANK_WINDOW_MB": "1"},  # ... with the bucketed scatter
