@@ -130,6 +130,9 @@ struct bwtc_cuda_ctx {
                                   // slower (a 9-bit pass costs +23%, 7 of them more than 8 eight-bit ones): kept as an
                                   // experiment, profiles/r02_experiments.md
   uint32_t status_row_words = 256;
+  int twopass = 0;                // BWTC_TWOPASS=1: with two L2 windows the second window is scattered by k_scatter_window from the
+                                  // rank words the first k_rerank launch stored in sorted order, instead of a second k_rerank
+                                  // launch (measured: Markov 32 MiB equal, source text -3%; the random scatter itself is the cost)
   int hybrid2 = 0;                // BWTC_HYBRID2=1: with two L2 windows, window 0 is written directly and window 1 staged + one
                                   // k_scatter_bucket, instead of one k_rerank launch per window (measured equal: 2.90 vs 2.88 ms)
   uint32_t rerank_pf_tiles = 0;   // k_rerank: L2 prefetch distance in tiles (BWTC_RERANK_PF; 0 = off)
@@ -448,6 +451,7 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
     rp.pf_tiles = ctx->rerank_pf_tiles;
     rp.ctr_slot = tile_slot(ctx, (uint32_t)CTR_RERANK);
     rp.nbuckets = nwin;
+    rp.nr_out = nullptr;
     rp.direct0 = hybrid2 ? 1u : 0u;
     rp.bucket_magic = (uint32_t)(((1ull << 32) + win_ids - 1) / win_ids);
     StageParams sp{stage_nr, stage_id, ctx->d_tilecnt, no_stage ? 0 : 1, ctx->d_idx[cur ^ 1], ctx->d_scat, woff};
@@ -463,10 +467,25 @@ int launch_rerank(bwtc_cuda_ctx* ctx, int cur, uint32_t m, uint32_t N, RerankPar
     ctx->stats.algorithmic_bytes += (uint64_t)m * (hybrid2 ? 8 : 16);  // staged (id, rank) pairs: written once, read once
     return 0;
   }
+  // Two windows: the first launch also leaves every record's new rank word beside its id (d_scat, idle here), and the
+  // second window is served by the light k_scatter_window instead of a second full re-rank.
+  const bool twopass = ctx->twopass && nwin == 2u && !(ROUND0 && rp.lazy);
   for (uint32_t w = 0; w < nwin; ++w) {
     rp.win_lo = (uint32_t)((uint64_t)N * w / nwin);
     rp.win_hi = (w + 1 == nwin) ? 0xFFFFFFFFu : (uint32_t)((uint64_t)N * (w + 1) / nwin);
-    rp.emit = ROUND0 ? (w == 0 ? 1u : 2u) : 0u;  // round 0: the first window launch emits every BWT byte (whole words)
+    rp.nr_out = (twopass && w == 0) ? ctx->d_scat : nullptr;
+    if (twopass && w == 1) {
+      const uint32_t grid = std::min<uint32_t>(div_up(m, 1024u), (uint32_t)ctx->sm_count * 8u);
+      const uint32_t mask = ROUND0 ? rp.id_mask : 0x7FFFFFFFu;
+      k_scatter_window<<<grid, 256, 0, st>>>(ctx->d_idx[cur], ctx->d_scat, m, mask, rp.win_lo, rp.win_hi, ctx->d_rank, ctx->d_ctrl());
+      CK(ctx, cudaGetLastError());
+      ctx->stats.kernel_launches++;
+      ctx->stats.algorithmic_bytes += (uint64_t)m * 12;  // rank words written once, ids + rank words read once
+      break;
+    }
+    // round 0: the first window launch emits every BWT byte (whole words); so does the only k_rerank launch of a two-pass
+    // scatter in any round; otherwise every window launch emits for its own ids
+    rp.emit = (ROUND0 || twopass) ? (w == 0 ? 1u : 2u) : 0u;
     rp.pf_tiles = ctx->rerank_pf_tiles;
     rp.ctr_slot = tile_slot(ctx, (uint32_t)(CTR_RERANK + w));
     rp.nbuckets = 0;
@@ -1555,6 +1574,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (const char* e = getenv("BWTC_LADDER_MORE")) c->ladder_more = std::max(1, atoi(e));
   if (const char* e = getenv("BWTC_LAZY")) c->use_lazy = atoi(e);
   if (const char* e = getenv("BWTC_HYBRID2")) c->hybrid2 = atoi(e);
+  if (const char* e = getenv("BWTC_TWOPASS")) c->twopass = atoi(e);
   if (const char* e = getenv("BWTC_RERANK_PF")) c->rerank_pf_tiles = (uint32_t)std::max(0, atoi(e));
   c->use_radix9 = env_radix9();
   c->status_row_words = status_row_words_for(c->use_radix9);

@@ -1055,6 +1055,9 @@ struct RerankParams {
   uint8_t decode[256];      // dense code -> byte (packed emission)
   uint32_t nbuckets;        // > 1: bucketed scatter — instead of writing rank[] the tile stages its (id, rank) pairs
   uint32_t bucket_magic;    //      grouped by id bucket (bucket = min(umulhi(id, magic), nbuckets-1)); see k_scatter_bucket
+  uint32_t* nr_out;         // != nullptr: additionally store every record's new rank word at its SORTED position (0xFFFFFFFF =
+                            // "rank unchanged"), coalesced; k_scatter_window then serves the other id windows from
+                            // (idx[], nr_out[]) without repeating the re-rank
   uint32_t direct0;         // bucketed: ids of bucket 0 are written to rank[] directly (its window stays L2-resident during
                             // this launch), only the other buckets are staged — the two-window case: one pass over the
                             // records + one k_scatter_bucket over half of the pairs, instead of two passes over the records
@@ -1063,8 +1066,9 @@ struct RerankParams {
   // rank is its sorted position and is looked up in the retained sorted keys when somebody needs it (rank_lookup).
   // 2 = materialise: write rank[] for the singletons only (the fallback out of lazy mode; nothing else is touched).
   uint32_t lazy;
-  // ROUND0: which records this launch emits BWT bytes for — 0: those whose id is in [win_lo, win_hi); 1: all (the first
-  // launch of a windowed scatter, so a thread's eight consecutive output bytes leave as one store); 2: none.
+  // Which records this launch emits BWT bytes for — 0: those whose id is in [win_lo, win_hi); 1: all (round 0: the first
+  // launch of a windowed scatter, so a thread's eight consecutive output bytes leave as one store; any round: the only
+  // k_rerank launch when k_scatter_window serves the other window); 2: none.
   uint32_t emit;
   // > 0: every CTA first asks L2 for the records of tile (mine + pf_tiles) — the tile a CTA launched about one wave later
   // will load; the kernel is bound by the latency of its up-front record loads (ncu: 49% of stall samples on their first use)
@@ -1543,6 +1547,7 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
   const bool bucketed = rp.nbuckets > 1;
   uint32_t live = 0, livemask = 0, gmax = 0, nrv[IPT];
   uint32_t wrmask = 0, bpos[IPT];
+  uint32_t anymask = 0;  // records whose rank word changed or became final (whatever their id window)
   uint32_t embits = 0, ew0 = 0, ew1 = 0;  // ROUND0: the BWT bytes of my eight (consecutive) sorted positions
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
@@ -1565,7 +1570,7 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
         changed = (HF != HH);
       }
       const bool in_win = (id[k] >= rp.win_lo) && (id[k] < rp.win_hi);
-      const bool emit_here = ROUND0 ? (rp.emit == 1u || (rp.emit == 0u && in_win)) : in_win;
+      const bool emit_here = rp.emit == 1u || (rp.emit == 0u && in_win);
       if (single && emit_here && !owns_hole(ep, id[k]) && !(LAZY && rp.lazy == 2u)) {  // emit L[nr] = T[id-1]
         uint8_t ch;
         if (ROUND0 && rp.packed) ch = s_dec[((k < 4 ? pc0 >> (8 * k) : pc1 >> (8 * (k - 4)))) & 0xFFu];
@@ -1580,6 +1585,7 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
       if (single) nr |= RANK_DONE;
       else if (sp.enable) { ++live; livemask |= 1u << k; gmax = max(gmax, j - HF + 1u); }
       nrv[k] = nr;
+      if (!ROUND0 && (changed || single)) anymask |= 1u << k;  // (round 0: every rank is new)
       bool wr = in_win && (changed || single);
       if (LAZY && rp.lazy) {
         const bool isshort = id[k] >= rp.short_thresh;
@@ -1639,6 +1645,20 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
         for (int k = 4; k < 8; ++k)
           if ((embits >> k) & 1u) emit_bwt(ep, j0 + k, (uint8_t)(ew1 >> (8 * (k - 4))));
       }
+    }
+  }
+  if (rp.nr_out) {
+    uint32_t v[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) v[k] = (ROUND0 || ((anymask >> k) & 1u)) ? nrv[k] : 0xFFFFFFFFu;
+    if (tile_base + TILE <= m) {
+      uint4* po = reinterpret_cast<uint4*>(rp.nr_out + j0);  // j0 % 8 == 0, buffer 256-byte aligned
+      __stcs(po, make_uint4(v[0], v[1], v[2], v[3]));
+      __stcs(po + 1, make_uint4(v[4], v[5], v[6], v[7]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < IPT; ++k)
+        if (j0 + k < m) rp.nr_out[j0 + k] = v[k];
     }
   }
   if (bucketed) {
@@ -1706,6 +1726,29 @@ __global__ void __launch_bounds__(256, (ROUND0 && !LAZY) ? 5 : 4) k_rerank(const
 // k_scatter_bucket — rank[id] = nr for the staged records of ONE id bucket (all tiles).  One warp per tile
 // segment; the bucket's slice of rank[] (<= ~72 MB) stays L2-resident, so the random 4-byte writes never pay a
 // DRAM sector fill + write-back, and — unlike re-running k_rerank once per window — every record is read once.
+// k_scatter_window — rank[id] = new rank for the records whose id lies in [win_lo, win_hi), from the sorted ids and the
+// rank words k_rerank left beside them (RerankParams::nr_out).  Sequential 128-bit reads, L2-resident random writes.
+__global__ void __launch_bounds__(256) k_scatter_window(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ nrw,
+                                                        uint32_t m, uint32_t id_mask, uint32_t win_lo, uint32_t win_hi,
+                                                        uint32_t* __restrict__ rank, const uint32_t* __restrict__ ctrl) {
+  if (ctrl[CTR_ERR]) return;  // sticky error: the rank words may be incomplete
+  const uint32_t quads = m >> 2;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+    const uint4 i4 = __ldcs(reinterpret_cast<const uint4*>(idx) + q);
+    const uint4 n4 = __ldcs(reinterpret_cast<const uint4*>(nrw) + q);
+    const uint32_t ii[4] = {i4.x & id_mask, i4.y & id_mask, i4.z & id_mask, i4.w & id_mask};
+    const uint32_t nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (nn[k] != 0xFFFFFFFFu && ii[k] >= win_lo && ii[k] < win_hi) rank[ii[k]] = nn[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (m & 3u)) {
+    const uint32_t j = (m & ~3u) + threadIdx.x;
+    const uint32_t i = idx[j] & id_mask, n = nrw[j];
+    if (n != 0xFFFFFFFFu && i >= win_lo && i < win_hi) rank[i] = n;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_scatter_bucket(const uint32_t* __restrict__ sc_id, const uint32_t* __restrict__ sc_nr,
                                                         const uint32_t* __restrict__ tile_woff, uint32_t ntiles,
                                                         uint32_t nbuckets, uint32_t b, uint32_t tile_records,

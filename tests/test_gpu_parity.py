@@ -298,6 +298,10 @@ ENGINE_KNOBS = [
     {"BWTC_RERANK_WINDOW_MB": "1", "BWTC_BUCKET_MIN_WINDOWS": "0"},  # one k_rerank launch per id window
     {"BWTC_RERANK_WINDOW_MB": "4", "BWTC_BUCKET_MIN_WINDOWS": "2"},  # bucketed scatter from two windows on
     {"BWTC_RERANK_WINDOW_MB": "6"},                                  # exactly two windows: one k_rerank launch per window
+    {"BWTC_RERANK_WINDOW_MB": "6", "BWTC_SEG": "0"},                 # ... in doubling rounds too
+    {"BWTC_RERANK_WINDOW_MB": "6", "BWTC_TWOPASS": "1"},             # exactly two windows: k_rerank + k_scatter_window (experiment, off)
+    {"BWTC_RERANK_WINDOW_MB": "6", "BWTC_TWOPASS": "1", "BWTC_SEG": "0"},
+    {"BWTC_RERANK_WINDOW_MB": "6", "BWTC_TWOPASS": "1", "BWTC_PACK_PRED": "0", "BWTC_AUX_MIN_MIB": "0"},
     {"BWTC_RERANK_WINDOW_MB": "6", "BWTC_HYBRID2": "1"},             # ... or window 0 direct, window 1 staged (experiment, off)
     {"BWTC_RERANK_WINDOW_MB": "6", "BWTC_HYBRID2": "1", "BWTC_SEG": "0"},  # the hybrid scatter in doubling rounds too
     {"BWTC_PACK_PRED": "0"},                                         # BWT characters gathered from the text
@@ -331,7 +335,9 @@ def test_every_engine_path_is_bit_exact(oracle, monkeypatch, knobs):
     n = (2 << 20) + 4097
     ctx = bw.CudaContext(n)
     rng = np.random.default_rng(77)
-    cases = [("markov", n), ("dna", n), ("repetitive", 1 << 20), ("random", n - 4099)]
+    # (the repetitive block keeps ~all suffixes live through its global doubling rounds: with n suffixes their rank scatter
+    # is windowed / bucketed exactly like round 0's)
+    cases = [("markov", n), ("dna", n), ("repetitive", 1 << 20), ("repetitive", n - 5), ("random", n - 4099)]
     try:
         for kind, sz in cases:
             x = bw.generate(kind, sz, seed=41)
