@@ -33,7 +33,8 @@ constexpr uint32_t RS_TILE64 = RS_BLOCK * RS_IPT64;
 constexpr uint32_t RS_TILE32 = RS_BLOCK * RS_IPT32;
 constexpr uint32_t AUX_TILE = 2048;  // k_pack_round0 / k_build_keys / k_rerank tile
 constexpr int MAX_PASSES = 8;
-constexpr uint32_t HIST_WORDS = MAX_PASSES * 512;  // digit histograms of one sort: pass p at p << rb (rb = 8 or 9 bits)
+constexpr uint32_t GRAM_OFF = MAX_PASSES * 512;    // the gram histogram of k_pack_round0 sits behind the digit histograms
+constexpr uint32_t HIST_WORDS = GRAM_OFF + (1u << GRAM_BITS);  // digit histograms of one sort: pass p at p << rb (rb = 8 or 9 bits)
 // Words per look-back status row: 256 (8-bit digits), 512 when the 9-bit digit passes are enabled (BWTC_RADIX9=1).
 inline uint32_t status_row_words_for(int use_radix9) { return use_radix9 ? 512u : 256u; }
 inline int env_radix9() { const char* e = getenv("BWTC_RADIX9"); return e ? atoi(e) : 0; }
@@ -130,6 +131,8 @@ struct bwtc_cuda_ctx {
                                   // slower (a 9-bit pass costs +23%, 7 of them more than 8 eight-bit ones): kept as an
                                   // experiment, profiles/r02_experiments.md
   uint32_t status_row_words = 256;
+  int use_gram = 1;               // round-0 digit histograms projected from one 12-bit gram histogram (6- and 3-bit codes; BWTC_GRAM=0:
+                                  // counted per digit class + k_hist_derive)
   int twopass = 0;                // BWTC_TWOPASS=1: with two L2 windows the second window is scattered by k_scatter_window from the
                                   // rank words the first k_rerank launch stored in sorted order, instead of a second k_rerank
                                   // launch (measured: Markov 32 MiB equal, source text -3%; the random scatter itself is the cost)
@@ -864,16 +867,40 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
         dp.count++;
       }
     }
+    // Gram mode (6- and 3-bit codes): one 4096-bin histogram of the keys' low 12 bits, every digit histogram projected
+    // from it (k_hist_from_gram) — one shared-memory atomic per key instead of one per counted digit.
+    GramParams gp;
+    gp.npass = 0;
+    bool use_gram = ctx->use_gram && !bs && N > 64 && (pl.bits == 6 || pl.bits == 3) && keybits >= (uint32_t)GRAM_BITS;
+    if (use_gram) {
+      const uint32_t W = (uint32_t)GRAM_BITS / pl.bits;
+      for (uint32_t p = 0; p < pl.npass && use_gram; ++p) {
+        const uint32_t lo = pl.rb * p;
+        const uint32_t u = std::min<uint32_t>(lo / pl.bits, pl.chars - W);
+        const uint32_t sft = lo - pl.bits * u;
+        // the digit must lie inside the 12 bits above bit (bits * u), or run past the top of the key (zeros there)
+        if (sft + pl.rb > (uint32_t)GRAM_BITS && lo + pl.rb <= keybits) use_gram = false;
+        if (sft >= 32u) use_gram = false;
+        gp.u[p] = (uint8_t)u;
+        gp.s[p] = (uint8_t)sft;
+      }
+      gp.npass = pl.npass;
+    }
+    uint32_t* gram = use_gram ? ctx->d_hist() + GRAM_OFF : nullptr;
+    if (use_gram) { hist_mask = 0; dp.count = 0; }
     if (pl.keybytes == 4) {
       k_pack_round0<uint32_t><<<grid, 256, 0, st>>>(d_text, N, static_cast<uint32_t*>(ctx->d_keys[0]), pl.pp,
-                                                     ctx->d_hist(), hist_mask, ptiles, pl.rb);
+                                                     ctx->d_hist(), hist_mask, ptiles, pl.rb, gram);
       if (dp.count) k_hist_derive<uint32_t><<<dp.count, 256, 0, st>>>(d_text, N, pl.pp, dp, ctx->d_hist(), pl.rb);
+      if (use_gram) k_hist_from_gram<uint32_t><<<gp.npass, 256, 0, st>>>(d_text, N, pl.pp, gp, gram, ctx->d_hist(), pl.rb);
     } else {
       k_pack_round0<unsigned long long><<<grid, 256, 0, st>>>(d_text, N, static_cast<unsigned long long*>(ctx->d_keys[0]),
-                                                               pl.pp, ctx->d_hist(), hist_mask, ptiles, pl.rb);
+                                                               pl.pp, ctx->d_hist(), hist_mask, ptiles, pl.rb, gram);
       if (dp.count) k_hist_derive<unsigned long long><<<dp.count, 256, 0, st>>>(d_text, N, pl.pp, dp, ctx->d_hist(), pl.rb);
+      if (use_gram)
+        k_hist_from_gram<unsigned long long><<<gp.npass, 256, 0, st>>>(d_text, N, pl.pp, gp, gram, ctx->d_hist(), pl.rb);
     }
-    if (dp.count) S.kernel_launches++;
+    if (dp.count || use_gram) S.kernel_launches++;
     CK(ctx, cudaGetLastError());
     S.kernel_launches++;
     S.algorithmic_bytes += (uint64_t)N + (uint64_t)N * pl.keybytes;
@@ -1575,6 +1602,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (const char* e = getenv("BWTC_LAZY")) c->use_lazy = atoi(e);
   if (const char* e = getenv("BWTC_HYBRID2")) c->hybrid2 = atoi(e);
   if (const char* e = getenv("BWTC_TWOPASS")) c->twopass = atoi(e);
+  if (const char* e = getenv("BWTC_GRAM")) c->use_gram = atoi(e);
   if (const char* e = getenv("BWTC_RERANK_PF")) c->rerank_pf_tiles = (uint32_t)std::max(0, atoi(e));
   c->use_radix9 = env_radix9();
   c->status_row_words = status_row_words_for(c->use_radix9);

@@ -377,16 +377,22 @@ struct PackParams {
   uint32_t stride;
 };
 
+constexpr int GRAM_BITS = 12;  // gram mode of k_pack_round0 / k_hist_from_gram (see GramParams)
+
 template <typename KeyT>
 __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__ text, uint32_t N,
                                                      KeyT* __restrict__ keys, PackParams pp,
                                                      uint32_t* __restrict__ hist, uint32_t hist_mask, uint32_t ntiles,
-                                                     uint32_t rb) {
+                                                     uint32_t rb, uint32_t* __restrict__ gram) {
   // rb: digit width of the sort that follows (8 or 9); digit p = (key >> rb*p) & (2^rb - 1), histogram p at hist + p * 2^rb
+  // gram != nullptr (hist_mask == 0): instead of digit histograms, ONE histogram of the low GRAM_BITS bits of every key —
+  // the last 2 (6-bit codes) or 4 (3-bit codes) characters of its window; every digit histogram is a projection of it
+  // (k_hist_from_gram).  One shared-memory atomic per key into 4096 bins instead of four into 256-bin histograms.
   constexpr int BLOCK = 256, IPT = 8, TILE = BLOCK * IPT;
   __shared__ uint8_t s_lut[256];
   __shared__ uint8_t s_code[TILE + 64];
-  __shared__ uint32_t s_hist[8 * 512];
+  __shared__ uint32_t s_hist[8 * 512];  // digit histograms, or the gram histogram (1 << GRAM_BITS bins)
+  static_assert((1 << GRAM_BITS) <= 8 * 512, "the gram histogram shares the digit histograms' shared memory");
   const int tid = threadIdx.x;
   const uint32_t dmask = (1u << rb) - 1u;
   s_lut[tid] = pp.lut[tid];
@@ -455,16 +461,29 @@ __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__
         for (int k = 0; k < IPT; ++k)
           if (t + k < N) keys[t + k] = out[k];
       }
+      if (gram) {
 #pragma unroll
-      for (int k = 0; k < IPT; ++k) {
-        if (t + k < N) {
+        for (int k = 0; k < IPT; ++k)
+          if (t + k < N) atomicAdd(&s_hist[(uint32_t)out[k] & ((1u << GRAM_BITS) - 1u)], 1u);
+      } else {
 #pragma unroll
-          for (int p = 0; p < (int)(sizeof(KeyT)); ++p)
-            if ((hist_mask >> p) & 1u) atomicAdd(&s_hist[(p << rb) + ((uint32_t)(out[k] >> (rb * p)) & dmask)], 1u);
+        for (int k = 0; k < IPT; ++k) {
+          if (t + k < N) {
+#pragma unroll
+            for (int p = 0; p < (int)(sizeof(KeyT)); ++p)
+              if ((hist_mask >> p) & 1u) atomicAdd(&s_hist[(p << rb) + ((uint32_t)(out[k] >> (rb * p)) & dmask)], 1u);
+          }
         }
       }
     }
     __syncthreads();
+  }
+  if (gram) {
+    for (uint32_t e = tid; e < (1u << GRAM_BITS); e += BLOCK) {
+      const uint32_t v = s_hist[e];
+      if (v) atomicAdd(&gram[e], v);
+    }
+    return;
   }
 #pragma unroll
   for (int p = 0; p < (int)(sizeof(KeyT)); ++p) {
@@ -488,6 +507,18 @@ __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__
 struct DeriveParams {
   uint32_t count;
   uint8_t p[8], r[8], t[8];
+};
+
+// Gram mode (6-bit and 3-bit codes): G[g] = number of suffixes whose key has g in its low GRAM_BITS bits = its last W
+// characters (W * b = 12).  Digit p of key(i) lies inside the W characters that start u_p characters above the key's low
+// end, and those are the LAST W characters of key(i - u_p) — the window slid by u_p positions, zero padding included, since
+// padding depends on the text position only.  So
+//   H_p[d] = sum_g G[g] [(g >> s_p) & dmask == d]  -  sum_{i = N-u_p}^{N-1} e((low12(key(i)) >> s_p) & dmask)   (no partner)
+//                                                  +  sum_{i = 0}^{u_p - 1} e(digit_p(key(i)))                    (not covered)
+// with 8p (or 9p) = b u_p + s_p, u_p capped so the W characters stay inside the key.  Block p of the grid builds H_p.
+struct GramParams {
+  uint32_t npass;
+  uint8_t u[8], s[8];
 };
 
 template <typename KeyT>
@@ -521,6 +552,33 @@ __global__ void __launch_bounds__(256) k_hist_derive(const uint8_t* __restrict__
       const KeyT kt = pack_key_at<KeyT>(text, N, N - 1u - (uint32_t)tid, s_lut, pp.bits, pp.chars);
       atomicSub(&s_h[(uint32_t)(kt >> (rb * r)) & dmask], 1u);
     }
+  }
+  __syncthreads();
+  for (uint32_t e = tid; e <= dmask; e += 256) hist[(p << rb) + e] = s_h[e];
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256) k_hist_from_gram(const uint8_t* __restrict__ text, uint32_t N, PackParams pp,
+                                                        GramParams gp, const uint32_t* __restrict__ gram,
+                                                        uint32_t* __restrict__ hist, uint32_t rb) {
+  __shared__ uint8_t s_lut[256];
+  __shared__ uint32_t s_h[512];
+  const int tid = threadIdx.x;
+  const uint32_t p = blockIdx.x, u = gp.u[p], sh = gp.s[p];
+  const uint32_t dmask = (1u << rb) - 1u;
+  s_lut[tid] = pp.lut[tid];
+  s_h[tid] = 0;
+  s_h[tid + 256] = 0;
+  __syncthreads();
+  for (uint32_t g = tid; g < (1u << GRAM_BITS); g += 256) {
+    const uint32_t v = gram[g];
+    if (v) atomicAdd(&s_h[(g >> sh) & dmask], v);
+  }
+  if ((uint32_t)tid < u && (uint32_t)tid < N) {
+    const KeyT kh = pack_key_at<KeyT>(text, N, (uint32_t)tid, s_lut, pp.bits, pp.chars);  // head: suffix tid, digit p directly
+    atomicAdd(&s_h[(uint32_t)(kh >> (rb * p)) & dmask], 1u);
+    const KeyT kt = pack_key_at<KeyT>(text, N, N - 1u - (uint32_t)tid, s_lut, pp.bits, pp.chars);  // tail: counted, no partner
+    atomicSub(&s_h[(((uint32_t)kt & ((1u << GRAM_BITS) - 1u)) >> sh) & dmask], 1u);
   }
   __syncthreads();
   for (uint32_t e = tid; e <= dmask; e += 256) hist[(p << rb) + e] = s_h[e];

@@ -110,6 +110,30 @@ def test_any_round0_key_shape_gives_identical_bytes(ctx, oracle, force):
     assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
 
 
+@pytest.mark.parametrize("gram", ["1", "0"])
+@pytest.mark.parametrize("sigma,force", [(8, (0, 0)), (8, (4, 4)), (7, (5, 4)), (8, (10, 4)), (5, (12, 8)), (8, (21, 8)),
+                                         (64, (2, 4)), (64, (3, 4)), (33, (7, 8)), (64, (10, 8))])
+def test_round0_histograms_from_the_gram_histogram(oracle, monkeypatch, gram, sigma, force):
+    """3-bit and 6-bit codes: k_pack_round0 counts ONE 4096-bin histogram of the keys' last 4 / 2 characters and every digit
+    histogram of the round-0 sort is projected from it (BWTC_GRAM=0: per-digit counting + k_hist_derive).  A wrong
+    histogram sends records to wrong places, so the bytes are the check; sizes with ragged tiles, text ending in the smallest
+    and in the largest symbol (the zero padding past the end is part of the windows that are counted)."""
+    monkeypatch.setenv("BWTC_GRAM", gram)
+    rng = np.random.default_rng(1000 + sigma)
+    for n, tail in ((70001, 0), (300007, sigma - 1), (65, 1)):
+        x = rng.integers(0, sigma, n).astype(np.uint8)
+        x[-30:] = tail
+        x[: sigma] = np.arange(sigma, dtype=np.uint8)  # every symbol present: the code width is what the case says
+        want = oracle.block(x, 8)
+        c = bw.CudaContext(n + 1)
+        c.set_round0(*force)
+        try:
+            got = _gpu_block(c, x, 8)
+        finally:
+            c.close()
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all() and (got[2] == want[2]).all(), (n, tail)
+
+
 @pytest.mark.parametrize("radix9", ["1", "0"])
 @pytest.mark.parametrize("kind,chars", [("markov", 6), ("markov", 7), ("markov", 8), ("markov", 9), ("markov", 10),
                                         ("dna", 17), ("dna", 22), ("dna", 27), ("dna", 31), ("dna", 32),
@@ -318,6 +342,7 @@ ENGINE_KNOBS = [
     {"BWTC_LAZY": "2", "BWTC_PACK_PRED": "0", "BWTC_AUX_MIN_MIB": "0"},
     {"BWTC_LAZY": "2", "BWTC_RERANK_WINDOW_MB": "1"},                # the fallback materialises ranks through the bucketed scatter
     {"BWTC_LAZY": "2", "BWTC_LADDER_FIRST": "0"},
+    {"BWTC_GRAM": "0"},                                              # round-0 histograms counted per digit class (default: gram)
     {"BWTC_RADIX9": "1"},                                            # 9-bit digit passes where they save a pass (experiment, default off)
     {"BWTC_RADIX9": "1", "BWTC_SEG": "0"},                           # ... in the doubling rounds too
     {"BWTC_RADIX9": "1", "BWTC_SEG": "0", "BWTC_STATIC_TILES": "0"},  # ... with tile tickets
