@@ -131,6 +131,7 @@ struct bwtc_cuda_ctx {
                                   // slower (a 9-bit pass costs +23%, 7 of them more than 8 eight-bit ones): kept as an
                                   // experiment, profiles/r02_experiments.md
   uint32_t status_row_words = 256;
+  int use_partial = 1;            // spare low bits of the round-0 key take the top bits of the next character (BWTC_PARTIAL=0: zeros)
   int use_gram = 1;               // round-0 digit histograms projected from one 12-bit gram histogram (6- and 3-bit codes; BWTC_GRAM=0:
                                   // counted per digit class + k_hist_derive)
   int twopass = 0;                // BWTC_TWOPASS=1: with two L2 windows the second window is scattered by k_scatter_window from the
@@ -213,6 +214,7 @@ void ctx_free(bwtc_cuda_ctx* c) {
 struct Round0Plan {
   uint32_t sigma, bits, chars, keybytes, npass;
   uint32_t rb;        // digit width of the round-0 sort: 9 when that saves a pass over 8-bit digits (64-bit keys only)
+  uint32_t rbits;     // spare low key bits filled with the top bits of character c+1 (PackParams::rbits)
   PackParams pp;
   bool has_memory;    // the 8-gram sample says the source is not i.i.d.-like (text, repeats)
   double live_pred;   // i.i.d.-like sources: predicted fraction of suffixes still tied after round 0, L(chars)
@@ -300,6 +302,17 @@ void plan_round0(const bwtc_cuda_ctx* ctx, const uint64_t* count, const bool* pr
     pl->rb = 9;
     pl->npass = div_up((uint64_t)chars * b + blk_bits, 9);
   }
+  {
+    // the digit passes cover rb * npass bits (at most the key width): what the c characters leave over takes the top bits
+    // of the next character (never a whole one: the chooser above already uses every whole character that fits)
+    const uint32_t covered = std::min<uint32_t>(pl->rb * pl->npass, keybytes * 8u);
+    const uint32_t used = chars * b + blk_bits;
+    uint32_t r = (ctx->use_partial && blk_bits == 0 && covered > used) ? covered - used : 0u;
+    if (r >= b) r = b - 1u;
+    if (chars >= 64u) r = 0;
+    pl->rbits = r;
+  }
+  pl->pp.rbits = pl->rbits;
   pl->pp.bits = b;
   pl->pp.chars = chars;
   pl->pp.nblocks = 1;
@@ -850,14 +863,18 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
     uint32_t hist_mask = 0;
     DeriveParams dp;
     dp.count = 0;
+    // (digit positions in the coordinates of the c exact characters: the key carries pl.rbits partial bits below them)
     const uint32_t keybits = pl.chars * pl.bits;
+    const uint32_t rbits = pl.rbits;
+    uint32_t regular_mask = 0;  // digits that lie entirely inside the exact characters
     for (uint32_t p = 0; p < pl.npass; ++p) {
       int rep = -1;
       const uint32_t rb = pl.rb;
-      const bool full_p = (rb * p + rb <= keybits);
+      const bool full_p = (rb * p >= rbits) && (rb * p - rbits + rb <= keybits);
+      if (full_p) regular_mask |= 1u << p;
       if (full_p && N > 64 && !bs)  // (a batch counts every digit directly: block numbers sit above the characters)
         for (uint32_t r = 0; r < p; ++r)
-          if (((hist_mask >> r) & 1u) && (rb * r) % pl.bits == (rb * p) % pl.bits && (rb * (p - r)) % pl.bits == 0) { rep = (int)r; break; }
+          if (((hist_mask >> r) & (regular_mask >> r) & 1u) && (rb * (p - r)) % pl.bits == 0) { rep = (int)r; break; }
       if (rep < 0) {
         hist_mask |= 1u << p;
       } else {
@@ -875,11 +892,21 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
     if (use_gram) {
       const uint32_t W = (uint32_t)GRAM_BITS / pl.bits;
       for (uint32_t p = 0; p < pl.npass && use_gram; ++p) {
-        const uint32_t lo = pl.rb * p;
-        const uint32_t u = std::min<uint32_t>(lo / pl.bits, pl.chars - W);
-        const uint32_t sft = lo - pl.bits * u;
-        // the digit must lie inside the 12 bits above bit (bits * u), or run past the top of the key (zeros there)
-        if (sft + pl.rb > (uint32_t)GRAM_BITS && lo + pl.rb <= keybits) use_gram = false;
+        uint32_t u, sft;
+        gp.next[p] = 0;
+        if (pl.rb * p < rbits) {  // the lowest digit reaches into the partial character: window of the following suffix
+          if (p != 0) use_gram = false;
+          u = 0;
+          sft = pl.bits - rbits;
+          gp.next[p] = 1;
+          if (sft + pl.rb > (uint32_t)GRAM_BITS) use_gram = false;
+        } else {
+          const uint32_t lo = pl.rb * p - rbits;
+          u = std::min<uint32_t>(lo / pl.bits, pl.chars - W);
+          sft = lo - pl.bits * u;
+          // the digit must lie inside the 12 bits above bit (bits * u), or run past the top of the key (zeros there)
+          if (sft + pl.rb > (uint32_t)GRAM_BITS && lo + pl.rb <= keybits) use_gram = false;
+        }
         if (sft >= 32u) use_gram = false;
         gp.u[p] = (uint8_t)u;
         gp.s[p] = (uint8_t)sft;
@@ -916,7 +943,7 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
   uint32_t id_bits = (uint32_t)ceil_log2_u64((uint64_t)N);
   if (id_bits < 1) id_bits = 1;
   const bool pack_pred = ctx->use_pack_pred && (id_bits + pl.bits <= 32) && (mask0 & 1u);
-  const uint32_t topshift = (pl.chars - 1) * pl.bits;
+  const uint32_t topshift = (pl.chars - 1) * pl.bits + pl.rbits;
   const uint32_t pred_mask = (1u << pl.bits) - 1u;  // (a batch key carries the block number above the characters)
   // No spare id bits (byte alphabets above 16 MiB) and a text too large for an L2-resident gather at emission time:
   // the predecessor codes travel as a one-byte payload array instead.
@@ -940,7 +967,7 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
   // its position in the sorted key array.  If a sample of the sorted keys says few suffixes stay in groups, rank[] is
   // written for those only and the others are looked up in the retained sorted keys when needed (rank_lookup).
   bool lazy = false;
-  const uint32_t keybits0 = pl.chars * pl.bits;
+  const uint32_t keybits0 = pl.chars * pl.bits + pl.rbits;
   if (ctx->use_lazy && !bs && !dbg_any(ctx) && N >= 64 && keybits0 >= 1) {
     // The decision needs no measurement: for an i.i.d.-like source (DNA, random bytes) the key-shape policy has already
     // predicted the fraction of suffixes still tied after round 0, L(c) = 1 - exp(-N 2^(-H0 c)) — it matches the measured
@@ -957,7 +984,8 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
     rp.m = N;
     {
       const uint32_t text_end = J.sentinel_outside_alphabet ? N - 1 : N;  // windows reaching text_end are unique
-      rp.short_thresh = pl.chars > text_end ? 0u : text_end - pl.chars + 1u;
+      const uint32_t wchars = pl.chars + (pl.rbits ? 1u : 0u);  // characters a key looks at (the partial one included)
+      rp.short_thresh = wchars > text_end ? 0u : text_end - wchars + 1u;
     }
     rp.lo_bits = 0;
     rp.lazy = lazy ? 1u : 0u;
@@ -977,6 +1005,7 @@ int64_t phase_sort(bwtc_cuda_ctx* ctx, Job& J) {
       L.N = N;
       L.bits = pl.bits;
       L.chars = pl.chars;
+      L.rbits = pl.rbits;
       L.tshift = keybits0 - tbits;
       memcpy(L.lut, pl.pp.lut, 256);
       CK(ctx, cudaMemcpyAsync(ctx->d_lookup, ctx->h_lookup, sizeof(LookupParams), cudaMemcpyHostToDevice, st));
@@ -1603,6 +1632,7 @@ int bwtc_cuda_ctx_create(bwtc_cuda_ctx** out, int device, uint32_t max_block_byt
   if (const char* e = getenv("BWTC_HYBRID2")) c->hybrid2 = atoi(e);
   if (const char* e = getenv("BWTC_TWOPASS")) c->twopass = atoi(e);
   if (const char* e = getenv("BWTC_GRAM")) c->use_gram = atoi(e);
+  if (const char* e = getenv("BWTC_PARTIAL")) c->use_partial = atoi(e);
   if (const char* e = getenv("BWTC_RERANK_PF")) c->rerank_pf_tiles = (uint32_t)std::max(0, atoi(e));
   c->use_radix9 = env_radix9();
   c->status_row_words = status_row_words_for(c->use_radix9);

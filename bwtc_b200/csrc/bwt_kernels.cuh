@@ -370,7 +370,11 @@ __global__ void __launch_bounds__(1024) k_window_pairs(const uint32_t* __restric
 struct PackParams {
   uint8_t lut[256];   // byte -> dense code
   uint32_t bits;      // b
-  uint32_t chars;     // c  (c*b <= 8*sizeof(KeyT), c <= 64)
+  uint32_t chars;     // c  (c*b + rbits <= 8*sizeof(KeyT), c <= 64)
+  // Spare low key bits (the last digit pass runs anyway) hold the TOP rbits bits of the code of character c+1: a monotone
+  // coarsening of that character, so key order still implies suffix order and equal keys still share c characters — the
+  // doubling distance stays c, but round 0 leaves fewer suffixes tied (Markov 32 MiB: 7.7% -> 3.0% with 4 of 6 bits).
+  uint32_t rbits;     // 0 <= rbits < b; 0 in batch mode
   // batch of nblocks > 1 blocks (text = concatenation, block k at k*stride): code 0 is RESERVED for the sentinel
   // positions (lut[] >= 1 for every data byte), and the block number is stored above the c characters
   uint32_t nblocks;
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint32_t t0 = tile * (uint32_t)TILE;
     const long long wlo = (long long)N - (long long)t0 - TILE;  // text index held in s_code[0]
-    for (int q = tid; q < TILE + 63; q += BLOCK) {
+    for (int q = tid; q < TILE + 64; q += BLOCK) {
       const long long g = wlo + q;
       s_code[q] = (g >= 0 && g < (long long)N) ? s_lut[text[g]] : (uint8_t)0;
     }
@@ -430,11 +434,14 @@ __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__
       KeyT key = 0;
       for (uint32_t j = 0; j < c; ++j) key = (KeyT)(key << b) | (KeyT)s_code[q0 + j];
       const uint32_t topshift = (c - 1) * b;
+      const uint32_t rbits = pp.rbits;
       KeyT out[IPT];
 #pragma unroll
       for (int k = 0; k < IPT; ++k) {
         if (k > 0) key = (KeyT)((KeyT)s_code[q0 - k] << topshift) | (KeyT)(key >> b);
         out[k] = key;
+        // (c <= 63 when rbits > 0, so q0 - k + c <= TILE + 62 is inside the loaded window)
+        if (rbits) out[k] = (KeyT)(key << rbits) | (KeyT)((uint32_t)s_code[q0 - k + (int)c] >> (b - rbits));
       }
       if (pp.nblocks > 1u) {  // block number above the characters: suffix of position t0+u0+k is N-1-(t0+u0+k)
         const uint32_t blkshift = c * b;
@@ -464,7 +471,7 @@ __global__ void __launch_bounds__(256) k_pack_round0(const uint8_t* __restrict__
       if (gram) {
 #pragma unroll
         for (int k = 0; k < IPT; ++k)
-          if (t + k < N) atomicAdd(&s_hist[(uint32_t)out[k] & ((1u << GRAM_BITS) - 1u)], 1u);
+          if (t + k < N) atomicAdd(&s_hist[(uint32_t)(out[k] >> pp.rbits) & ((1u << GRAM_BITS) - 1u)], 1u);
       } else {
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
@@ -516,18 +523,27 @@ struct DeriveParams {
 //   H_p[d] = sum_g G[g] [(g >> s_p) & dmask == d]  -  sum_{i = N-u_p}^{N-1} e((low12(key(i)) >> s_p) & dmask)   (no partner)
 //                                                  +  sum_{i = 0}^{u_p - 1} e(digit_p(key(i)))                    (not covered)
 // with 8p (or 9p) = b u_p + s_p, u_p capped so the W characters stay inside the key.  Block p of the grid builds H_p.
+// With partial bits (PackParams::rbits) everything above is in the coordinates of E = key >> rbits, the c exact characters:
+// G counts the low 12 bits of E, digit p is E bits [rb p - rbits, ...).  The lowest digit then reaches below E into the
+// partial character: its 12-bit window is the low window of E(i + 1) (u = -1, flag below) and
+//   H_0 = projection(G) - e(window of suffix 0) + e(window of the all-padding "suffix N" = 0).
 struct GramParams {
   uint32_t npass;
   uint8_t u[8], s[8];
+  uint8_t next[8];  // 1: u = -1 (the window of the following suffix)
 };
 
 template <typename KeyT>
 __device__ __forceinline__ KeyT pack_key_at(const uint8_t* __restrict__ text, uint32_t N, uint32_t i, const uint8_t* lut,
-                                            uint32_t b, uint32_t c) {
+                                            uint32_t b, uint32_t c, uint32_t rbits) {
   KeyT key = 0;
   for (uint32_t j = 0; j < c; ++j) {
     const uint32_t g = i + j;
     key = (KeyT)(key << b) | (KeyT)((g < N) ? lut[text[g]] : 0u);
+  }
+  if (rbits) {
+    const uint32_t g = i + c;
+    key = (KeyT)(key << rbits) | (KeyT)(((g < N) ? (uint32_t)lut[text[g]] : 0u) >> (b - rbits));
   }
   return key;
 }
@@ -545,11 +561,11 @@ __global__ void __launch_bounds__(256) k_hist_derive(const uint8_t* __restrict__
   __syncthreads();
   if ((uint32_t)tid < t) {
     if ((uint32_t)tid < N) {  // head term: suffix i = tid counted for digit p
-      const KeyT kh = pack_key_at<KeyT>(text, N, (uint32_t)tid, s_lut, pp.bits, pp.chars);
+      const KeyT kh = pack_key_at<KeyT>(text, N, (uint32_t)tid, s_lut, pp.bits, pp.chars, pp.rbits);
       atomicAdd(&s_h[(uint32_t)(kh >> (rb * p)) & dmask], 1u);
     }
     if ((uint32_t)tid < N) {  // tail term: suffix i = N-1-tid was counted for digit r but has no partner
-      const KeyT kt = pack_key_at<KeyT>(text, N, N - 1u - (uint32_t)tid, s_lut, pp.bits, pp.chars);
+      const KeyT kt = pack_key_at<KeyT>(text, N, N - 1u - (uint32_t)tid, s_lut, pp.bits, pp.chars, pp.rbits);
       atomicSub(&s_h[(uint32_t)(kt >> (rb * r)) & dmask], 1u);
     }
   }
@@ -574,11 +590,17 @@ __global__ void __launch_bounds__(256) k_hist_from_gram(const uint8_t* __restric
     const uint32_t v = gram[g];
     if (v) atomicAdd(&s_h[(g >> sh) & dmask], v);
   }
-  if ((uint32_t)tid < u && (uint32_t)tid < N) {
-    const KeyT kh = pack_key_at<KeyT>(text, N, (uint32_t)tid, s_lut, pp.bits, pp.chars);  // head: suffix tid, digit p directly
+  if (gp.next[p]) {
+    if (tid == 0) {
+      const KeyT k0 = pack_key_at<KeyT>(text, N, 0u, s_lut, pp.bits, pp.chars, pp.rbits);
+      atomicSub(&s_h[(((uint32_t)(k0 >> pp.rbits) & ((1u << GRAM_BITS) - 1u)) >> sh) & dmask], 1u);
+      atomicAdd(&s_h[0], 1u);
+    }
+  } else if ((uint32_t)tid < u && (uint32_t)tid < N) {
+    const KeyT kh = pack_key_at<KeyT>(text, N, (uint32_t)tid, s_lut, pp.bits, pp.chars, pp.rbits);  // head: suffix tid, digit p directly
     atomicAdd(&s_h[(uint32_t)(kh >> (rb * p)) & dmask], 1u);
-    const KeyT kt = pack_key_at<KeyT>(text, N, N - 1u - (uint32_t)tid, s_lut, pp.bits, pp.chars);  // tail: counted, no partner
-    atomicSub(&s_h[(((uint32_t)kt & ((1u << GRAM_BITS) - 1u)) >> sh) & dmask], 1u);
+    const KeyT kt = pack_key_at<KeyT>(text, N, N - 1u - (uint32_t)tid, s_lut, pp.bits, pp.chars, pp.rbits);  // tail: counted, no partner
+    atomicSub(&s_h[(((uint32_t)(kt >> pp.rbits) & ((1u << GRAM_BITS) - 1u)) >> sh) & dmask], 1u);
   }
   __syncthreads();
   for (uint32_t e = tid; e <= dmask; e += 256) hist[(p << rb) + e] = s_h[e];
@@ -1145,6 +1167,7 @@ struct LookupParams {
   const uint32_t* livebits;  // bit i set: rank[i] is valid
   const uint8_t* text;
   uint32_t N, bits, chars, tshift;
+  uint32_t rbits;            // PackParams::rbits of the round-0 keys
   uint8_t lut[256];
 };
 
@@ -1196,6 +1219,10 @@ __device__ __forceinline__ uint32_t rank_lookup(const LookupParams& lk, const ui
   for (uint32_t c = 0; c < lk.chars; ++c) {
     const uint32_t g = j + c;
     key = (key << lk.bits) | (unsigned long long)((g < lk.N) ? lk.lut[lk.text[g]] : 0u);
+  }
+  if (lk.rbits) {
+    const uint32_t g = j + lk.chars;
+    key = (key << lk.rbits) | (unsigned long long)(((g < lk.N) ? (uint32_t)lk.lut[lk.text[g]] : 0u) >> (lk.bits - lk.rbits));
   }
   const uint32_t p = (uint32_t)(key >> lk.tshift);
   uint32_t lo = lk.ktab[p], hi = lk.ktab[p + 1u];
